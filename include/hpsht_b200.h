@@ -1,0 +1,173 @@
+/*
+ * hpsht_b200.h — C ABI of the B200-native spherical-harmonic-transform library that
+ * replaces the Ducc0.jl + MPI.Alltoallv! seam of HealpixMPI.jl's hot path
+ * (alm2map! / adjoint_alm2map! on DAlm{RR} / DMap{RR}; reference src/sht.jl:75-94, 165-179).
+ *
+ * Conventions
+ *   - Every function returns int: 0 = success, non-zero = error; hpsht_last_error() gives the
+ *     thread-local message.  Nothing throws across the boundary, nothing calls exit().
+ *   - All index arrays at this boundary are 0-BASED (the Julia shim subtracts 1 from
+ *     info.mstart / info.rstart exactly like Ducc0.jl's glue does).
+ *   - Arrays use the memory order Julia hands over (column-major, first index fastest):
+ *       alm  (nalm_loc, ncomp)           ->  alm[comp*alm_cstride + i]        complex128 (re,im)
+ *       map  (npix_loc, ncomp)           ->  map[comp*map_cstride + p]        float64
+ *       leg  alm-side (nm_loc, nring, ncomp) -> leg[(comp*nring + ir)*nm_loc + mi]   complex128
+ *       leg  map-side (nm_tot, nring_loc, ncomp) -> leg[(comp*nring_loc + ir)*nm_tot + m]
+ *   - Every data pointer may be a HOST pointer or a DEVICE pointer (cudaMalloc'd on the
+ *     plan's device); the library detects which (cudaPointerGetAttributes) and stages
+ *     host buffers through pinned memory.  Small descriptor arrays (mval, mstart, theta,
+ *     nphi, phi0, ringstart) are always HOST pointers.
+ *   - ncomp == 1  <=> spin 0 ; ncomp == 2 <=> spin 2 with (E,B) <-> (Q,U)   (src/sht.jl:84).
+ *   - nthreads is accepted for signature parity with the reference and ignored.
+ *   - Calls are synchronous (device work is complete on return) unless stated otherwise.
+ *   - The product path is CUDA only: without a usable sm_100 device the compute entry
+ *     points fail with HPSHT_ERR_CUDA; there is no CPU fallback.
+ */
+#ifndef HPSHT_B200_H
+#define HPSHT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPSHT_VERSION_MAJOR 0
+#define HPSHT_VERSION_MINOR 1
+
+enum {
+  HPSHT_OK = 0,
+  HPSHT_ERR_ARG = 1,      /* invalid argument (DomainError on the Julia side)            */
+  HPSHT_ERR_CUDA = 2,     /* CUDA runtime failure, or no usable device                   */
+  HPSHT_ERR_NCCL = 3,     /* NCCL failure / libnccl not loadable                         */
+  HPSHT_ERR_UNSUPPORTED = 4, /* e.g. ring length not a multiple of 4, lstride != 1       */
+  HPSHT_ERR_EMPTY_RANK = 5,  /* a rank would own no m or no ring (src/alm.jl:168, src/map.jl:162) */
+  HPSHT_ERR_INTERNAL = 6
+};
+
+/* ------------------------------------------------------------------------------------ */
+/* 0. Library info / errors                                                             */
+/* ------------------------------------------------------------------------------------ */
+int         hpsht_version(void);              /* major*100 + minor                                 */
+const char* hpsht_last_error(void);           /* thread-local, valid until the next call on thread */
+int         hpsht_device_count(int* count);   /* number of CUDA devices visible (0 on a CPU box)   */
+
+/* ------------------------------------------------------------------------------------ */
+/* 1. Round-robin bookkeeping (integer-exact restatement; host only, no CUDA needed)    */
+/*    replaces src/alm.jl:102-151 and src/map.jl:99-143.                                */
+/* ------------------------------------------------------------------------------------ */
+/* get_nm_RR        (src/alm.jl:102-105): number of m owned by task_rank                */
+int hpsht_rr_nm(int64_t mmax, int task_rank, int c_size, int64_t* nm);
+/* get_mval_RR      (src/alm.jl:112-119): mval[i] = task_rank + i*c_size, i<nm          */
+int hpsht_rr_mval(int64_t mmax, int task_rank, int c_size, int64_t* mval /*[nm]*/);
+/* get_m_tasks_RR   (src/alm.jl:127-133): task[m] = m % c_size, m=0..mmax               */
+int hpsht_rr_m_tasks(int64_t mmax, int c_size, int64_t* task /*[mmax+1]*/);
+/* make_mstart_complex (src/alm.jl:141-151) but 0-BASED: alm[mstart[mi] + l] = a_{l,mval[mi]}.
+   (Julia's 1-based value is this + 1.)                                                */
+int hpsht_rr_mstart(int64_t lmax, int64_t stride, int64_t nm, const int64_t* mval,
+                    int64_t* mstart /*[nm]*/);
+/* get_nrings_RR    (src/map.jl:99-102): eq_idx = 2*nside                               */
+int hpsht_rr_nrings(int64_t eq_idx, int task_rank, int c_size, int64_t* nrings);
+/* get_rindexes_RR  (src/map.jl:113-121): 1-BASED global ring ids, equator outwards N,S */
+int hpsht_rr_rindexes(int64_t eq_idx, int task_rank, int c_size, int64_t* rings /*[nrings]*/);
+/* get_rindexes_tot_RR (src/map.jl:134-143): concatenation over ranks, length 2*eq_idx-1 */
+int hpsht_rr_rindexes_tot(int64_t eq_idx, int c_size, int64_t* rings /*[2*eq_idx-1]*/);
+/* all-to-all counts of communicate_alm2map! (src/sht.jl:20-27), in complex elements per
+   component: send[t] = nm(rank)*nrings(t), recv[t] = nrings(rank)*nm(t)                 */
+int hpsht_rr_a2a_counts(int64_t mmax, int64_t eq_idx, int task_rank, int c_size,
+                        int64_t* send /*[c_size]*/, int64_t* recv /*[c_size]*/);
+
+/* HEALPix RING-scheme geometry of one ring (1-based ring id 1..4*nside-1); what
+   Healpix.getringinfo!/pix2ang provide to ScatterMap! (src/map.jl:177-183).
+   first_pix is the 0-based RING index of the ring's first pixel.                       */
+int hpsht_healpix_ring(int64_t nside, int64_t ring, int64_t* nphi, double* theta,
+                       double* phi0, int64_t* first_pix);
+
+/* ------------------------------------------------------------------------------------ */
+/* 2. Stage-level entry points — 1:1 with the four Ducc0.Sht calls of src/sht.jl        */
+/* ------------------------------------------------------------------------------------ */
+/* Ducc0.Sht.alm2leg!(alm, leg, spin, lmax, mval, mstart, lstride, theta, nthreads)
+   (src/sht.jl:85).  leg[(comp*nring+ir)*nm + mi] = sum_l alm-term * lambda(theta[ir]).  */
+int hpsht_alm2leg(const double* alm, int64_t alm_cstride, double* leg, int spin,
+                  int64_t lmax, int64_t nm, const int64_t* mval, const int64_t* mstart,
+                  int64_t lstride, int64_t nring, const double* theta, int nthreads);
+/* Ducc0.Sht.leg2alm!(leg, alm, spin, lmax, mval, mstart, lstride, theta, nthreads)
+   (src/sht.jl:178): adjoint of the above.  Entries of alm with l < spin are set to 0.   */
+int hpsht_leg2alm(const double* leg, double* alm, int64_t alm_cstride, int spin,
+                  int64_t lmax, int64_t nm, const int64_t* mval, const int64_t* mstart,
+                  int64_t lstride, int64_t nring, const double* theta, int nthreads);
+/* Ducc0.Sht.leg2map!(leg, map, nphi, phi0, ringstart, pixstride, nthreads) (src/sht.jl:93)
+   leg is map-side: (nm, nring, ncomp) with m = 0..nm-1 contiguous.                      */
+int hpsht_leg2map(const double* leg, double* map, int64_t map_cstride, int ncomp,
+                  int64_t nm, int64_t nring, const int64_t* nphi, const double* phi0,
+                  const int64_t* ringstart, int64_t pixstride, int nthreads);
+/* Ducc0.Sht.map2leg!(map, leg, nphi, phi0, ringstart, pixstride, nthreads) (src/sht.jl:169) */
+int hpsht_map2leg(const double* map, int64_t map_cstride, double* leg, int ncomp,
+                  int64_t nm, int64_t nring, const int64_t* nphi, const double* phi0,
+                  const int64_t* ringstart, int64_t pixstride, int nthreads);
+
+/* ------------------------------------------------------------------------------------ */
+/* 3. Fused plan — owns leg buffers, tables, streams and the NCCL communicator.          */
+/*    alm2map!(d_alm, d_map) / adjoint_alm2map!(d_map, d_alm)  (src/sht.jl:75-100,165-185)*/
+/* ------------------------------------------------------------------------------------ */
+typedef struct hpsht_plan hpsht_plan;
+
+#define HPSHT_NCCL_ID_BYTES 128
+/* rank 0 calls this and ships the 128 bytes to the other ranks (MPI.bcast in Julia,
+   torch.distributed / file store in the Python harness).                                */
+int hpsht_nccl_unique_id(unsigned char id[HPSHT_NCCL_ID_BYTES]);
+
+/* Collective over the n_ranks processes.  The RR geometry (which m, which rings, all
+   descriptor arrays of AlmInfoMPI / GeomInfoMPI) is derived inside from (nside,lmax,rank,
+   n_ranks) and must equal what Scatter! builds (src/alm.jl:159-176, src/map.jl:151-197).
+   device < 0: use the current CUDA device.  nccl_id may be NULL iff n_ranks == 1.
+   max_ncomp (1 or 2) sizes the internal leg buffers.                                    */
+int hpsht_plan_create(hpsht_plan** plan, int64_t nside, int64_t lmax, int rank, int n_ranks,
+                      const unsigned char* nccl_id, int device, int max_ncomp);
+int hpsht_plan_destroy(hpsht_plan* plan);
+
+/* Sizes and descriptor arrays of this rank's shard (so callers can cross-check them
+   against DAlm.info / DMap.info).  Any output pointer may be NULL.                      */
+int hpsht_plan_sizes(const hpsht_plan* plan, int64_t* nm_loc, int64_t* nalm_loc,
+                     int64_t* nring_loc, int64_t* npix_loc, int64_t* nring_tot);
+int hpsht_plan_alm_info(const hpsht_plan* plan, int64_t* mval, int64_t* mstart /*0-based*/);
+int hpsht_plan_map_info(const hpsht_plan* plan, int64_t* rings /*1-based ids*/,
+                        int64_t* rstart /*0-based*/, int64_t* nphi, double* theta,
+                        double* phi0, double* thetatot /*[nring_tot]*/);
+
+/* alm (nalm_loc, ncomp) complex128 -> map (npix_loc, ncomp) float64.  Host or device
+   pointers (see top).  Collective.                                                      */
+int hpsht_alm2map(hpsht_plan* plan, const double* alm, double* map, int ncomp, int nthreads);
+/* map -> alm, exact transpose Y^T (no quadrature weights).  Collective.                */
+int hpsht_adjoint_alm2map(hpsht_plan* plan, const double* map, double* alm, int ncomp,
+                          int nthreads);
+
+/* Per-stage device times (ms, CUDA events) of the most recent fused call on this plan:
+   [0] total, [1] alm prep/post, [2] Legendre, [3] all-to-all (+pack/unpack transposes),
+   [4] ring FFT, [5] H2D, [6] D2H.                                                       */
+#define HPSHT_NTIMES 8
+int hpsht_plan_timings(const hpsht_plan* plan, double ms[HPSHT_NTIMES]);
+/* Number of kernel launches issued by the most recent fused call.                       */
+int hpsht_plan_launches(const hpsht_plan* plan, int64_t* n);
+/* Algorithmic Legendre work of this rank for a given spin (0 or 2): number of
+   (l, m, ring-pair) recurrence steps after the m <= mlim(theta) cut.         */
+int hpsht_plan_legendre_steps(const hpsht_plan* plan, int spin, double* steps_culled,
+                              double* steps_dense);
+
+/* Device-memory helpers so a host language without a CUDA binding can keep shards
+   resident.                                                                 */
+int hpsht_device_malloc(void** dptr, size_t bytes);
+int hpsht_device_free(void* dptr);
+int hpsht_memcpy_h2d(void* dptr, const void* hptr, size_t bytes);
+int hpsht_memcpy_d2h(void* hptr, const void* dptr, size_t bytes);
+int hpsht_device_synchronize(void);
+
+/* FP64 FMA micro-benchmark (no FP64 entry in MEASURED_PEAKS.json): returns sustained
+   TFLOP/s of dependent-chain-free DFMA on the current device.                           */
+int hpsht_measure_fp64_peak(double* tflops, double* seconds_run);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPSHT_B200_H */
