@@ -1,0 +1,846 @@
+// api.cu — the C ABI (include/hpsht_b200.h): round-robin bookkeeping, the four stage-level entry
+// points that mirror the Ducc0.Sht calls of reference src/sht.jl:85,93,169,178, and the fused plan
+// that owns the leg buffers, the RR geometry and the NCCL exchange replacing MPI.Alltoallv!
+// (src/sht.jl:32,133).
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+#include "legendre.cuh"
+#include "nccl_dyn.hpp"
+#include "ringfft.cuh"
+#include "rr.hpp"
+
+namespace hpsht {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+void require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    throw Error(HPSHT_ERR_CUDA,
+                "no CUDA device available: libhpsht_b200 has no CPU fallback (the product path is "
+                "sm_100a kernels only)");
+  }
+}
+
+// ---- exchange pack / unpack (map-side leg <-> per-peer blocks) ----
+// legF[(comp*nr_loc + j)*nm_tot + (s + P*i)]  <->  blk_s[(comp*nr_loc + j)*nm_s + i]
+__global__ void k_unpack(const double2* __restrict__ mapside, const int64_t* __restrict__ boff,
+                         double2* __restrict__ legF, int64_t nm_tot, int64_t nr_loc, int ncomp, int P,
+                         int64_t mmax) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = blockIdx.y;  // comp*nr_loc + j
+  if (m >= nm_tot) return;
+  const int s = (int)(m % P);
+  const int64_t i = m / P;
+  const int64_t nm_s = (mmax + P - s) / P;
+  legF[row * nm_tot + m] = mapside[boff[s] + row * nm_s + i];
+}
+__global__ void k_pack(const double2* __restrict__ legF, const int64_t* __restrict__ boff,
+                       double2* __restrict__ mapside, int64_t nm_tot, int64_t nr_loc, int ncomp, int P,
+                       int64_t mmax) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = blockIdx.y;
+  if (m >= nm_tot) return;
+  const int s = (int)(m % P);
+  const int64_t i = m / P;
+  const int64_t nm_s = (mmax + P - s) / P;
+  mapside[boff[s] + row * nm_s + i] = legF[row * nm_tot + m];
+}
+
+// ---- FP64 FMA peak probe: 8 independent chains per thread, no memory traffic ----
+__global__ void k_dfma_peak(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5,
+         a6 = seed + 6, a7 = seed + 7;
+  const double x = 0.999999, y = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, x, y);
+      a1 = fma(a1, x, y);
+      a2 = fma(a2, x, y);
+      a3 = fma(a3, x, y);
+      a4 = fma(a4, x, y);
+      a5 = fma(a5, x, y);
+      a6 = fma(a6, x, y);
+      a7 = fma(a7, x, y);
+    }
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+
+struct Timer {
+  cudaEvent_t ev[16];
+  Timer() {
+    for (auto& e : ev) cudaEventCreate(&e);
+  }
+  ~Timer() {
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+};
+
+}  // namespace
+
+// =================================================================================================
+// plan
+// =================================================================================================
+}  // namespace hpsht
+
+using namespace hpsht;
+
+struct hpsht_plan {
+  int64_t nside = 0, lmax = 0;
+  int rank = 0, P = 1, device = 0, max_ncomp = 1;
+  // RR shard description (what Scatter! builds: src/alm.jl:159-176, src/map.jl:151-197)
+  std::vector<int64_t> mval, mstart, rings, rstart, nphi;
+  std::vector<double> theta, phi0, thetatot;
+  std::vector<int64_t> nr_of, nm_of;  // per rank
+  int64_t nm_loc = 0, nalm_loc = 0, nr_loc = 0, npix_loc = 0, nr_tot = 0, nm_tot = 0;
+  bool stages_ready = false;
+
+  cudaStream_t stream = nullptr;
+  LegendreStage leg;
+  RingFFT fft;
+  DevBuf<double> legF;      // map-side leg [ncomp][nr_loc][nm_tot] (complex)
+  DevBuf<double> almside;   // P>1: per-peer blocks [comp][nr_t][nm_loc]
+  DevBuf<double> mapside;   // P>1: per-peer blocks [comp][nr_loc][nm_s]
+  std::vector<int64_t> aoff, boff;  // block offsets in complex elements (max_ncomp sized)
+  DevBuf<int64_t> d_boff;
+  DevBuf<double> stage_alm, stage_map;  // device staging for host-pointer calls
+  ncclComm_t comm = nullptr;
+  std::unique_ptr<Timer> tm;
+  double ms[HPSHT_NTIMES] = {0};
+  int64_t n_launch = 0;
+
+  void build_shard();
+  void ensure_stages();
+  void exchange(bool synthesis, int ncomp);
+  void run(bool synthesis, const double* in, double* out, int ncomp);
+};
+
+void hpsht_plan::build_shard() {
+  const int64_t eq = 2 * nside;
+  HP_REQUIRE(nside >= 1 && lmax >= 0, HPSHT_ERR_ARG, "nside >= 1 and lmax >= 0 required");
+  HP_REQUIRE(rank >= 0 && rank < P, HPSHT_ERR_ARG, "rank can not exceed communicator size");
+  mval = rr_mval(lmax, rank, P);
+  HP_REQUIRE(!mval.empty(), HPSHT_ERR_EMPTY_RANK, std::to_string(rank) + "-th task is empty.");
+  mstart = rr_mstart0(lmax, 1, mval);
+  rings = rr_rindexes(eq, rank, P);
+  HP_REQUIRE(!rings.empty(), HPSHT_ERR_EMPTY_RANK, std::to_string(rank) + "-th MPI task has no rings.");
+  nm_loc = (int64_t)mval.size();
+  nalm_loc = 0;
+  for (int64_t m : mval) nalm_loc += lmax + 1 - m;
+  nr_loc = (int64_t)rings.size();
+  nm_tot = lmax + 1;
+  nr_tot = 2 * eq - 1;
+  rstart.resize((size_t)nr_loc);
+  nphi.resize((size_t)nr_loc);
+  theta.resize((size_t)nr_loc);
+  phi0.resize((size_t)nr_loc);
+  npix_loc = 0;
+  for (int64_t i = 0; i < nr_loc; ++i) {
+    RingGeom g = healpix_ring(nside, rings[(size_t)i]);
+    rstart[(size_t)i] = npix_loc;
+    nphi[(size_t)i] = g.nphi;
+    theta[(size_t)i] = g.theta;
+    phi0[(size_t)i] = g.phi0;
+    npix_loc += g.nphi;
+  }
+  std::vector<int64_t> tot = rr_rindexes_tot(eq, P);
+  thetatot.resize(tot.size());
+  for (size_t i = 0; i < tot.size(); ++i) thetatot[i] = healpix_ring(nside, tot[i]).theta;
+  nr_of.resize((size_t)P);
+  nm_of.resize((size_t)P);
+  for (int t = 0; t < P; ++t) {
+    nr_of[(size_t)t] = rr_nrings(eq, t, P);
+    nm_of[(size_t)t] = rr_nm(lmax, t, P);
+    HP_REQUIRE(nr_of[(size_t)t] > 0 && nm_of[(size_t)t] > 0, HPSHT_ERR_EMPTY_RANK,
+               std::to_string(t) + "-th task is empty.");
+  }
+}
+
+void hpsht_plan::ensure_stages() {
+  if (stages_ready) return;
+  // ---- leg layout seen by the Legendre kernels: ring slots in thetatot order ----
+  LegLayout lay;
+  lay.base.resize((size_t)nr_tot);
+  lay.mstride.assign((size_t)nr_tot, 1);
+  lay.cstride.resize((size_t)nr_tot);
+  if (P == 1) {
+    // single rank: the Legendre stage reads/writes the map-side array directly (src/sht.jl:87-88)
+    for (int64_t s = 0; s < nr_tot; ++s) {
+      lay.base[(size_t)s] = s * nm_tot;
+      lay.cstride[(size_t)s] = nr_loc * nm_tot;
+    }
+    legF.alloc((size_t)max_ncomp * nr_loc * nm_tot * 2);
+  } else {
+    aoff.assign((size_t)P + 1, 0);
+    boff.assign((size_t)P + 1, 0);
+    for (int t = 0; t < P; ++t) {
+      aoff[(size_t)t + 1] = aoff[(size_t)t] + (int64_t)max_ncomp * nr_of[(size_t)t] * nm_loc;
+      boff[(size_t)t + 1] = boff[(size_t)t] + (int64_t)max_ncomp * nr_loc * nm_of[(size_t)t];
+    }
+    int64_t s = 0;
+    for (int t = 0; t < P; ++t)
+      for (int64_t j = 0; j < nr_of[(size_t)t]; ++j, ++s) {
+        lay.base[(size_t)s] = aoff[(size_t)t] + j * nm_loc;
+        lay.cstride[(size_t)s] = nr_of[(size_t)t] * nm_loc;
+      }
+    almside.alloc((size_t)aoff[(size_t)P] * 2);
+    mapside.alloc((size_t)boff[(size_t)P] * 2);
+    legF.alloc((size_t)max_ncomp * nr_loc * nm_tot * 2);
+    d_boff.upload(boff.data(), boff.size(), stream);
+  }
+  leg.setup(lmax, mval.data(), mstart.data(), nm_loc, nr_tot, thetatot.data(), lay, max_ncomp, stream);
+  fft.setup(nr_loc, nphi.data(), phi0.data(), rstart.data(), nm_tot, stream);
+  HP_CUDA(cudaStreamSynchronize(stream));
+  stages_ready = true;
+}
+
+// m-sharded <-> ring-sharded transpose of the leg array (communicate_alm2map! / communicate_map2alm!,
+// src/sht.jl:5-44,106-135), all components in one grouped NCCL send/recv exchange.
+void hpsht_plan::exchange(bool synthesis, int ncomp) {
+  NcclApi& N = NcclApi::get();
+  double* A = almside.p;
+  double* B = mapside.p;
+  HP_NCCL(N.GroupStart());
+  for (int t = 0; t < P; ++t) {
+    const size_t na = (size_t)ncomp * nr_of[(size_t)t] * nm_loc * 2;  // doubles, alm-side block t
+    const size_t nb = (size_t)ncomp * nr_loc * nm_of[(size_t)t] * 2;  // doubles, map-side block t
+    double* pa = A + (size_t)aoff[(size_t)t] * 2;
+    double* pb = B + (size_t)boff[(size_t)t] * 2;
+    if (t == rank) continue;
+    if (synthesis) {
+      HP_NCCL(N.Send(pa, na, ncclDouble, t, comm, stream));
+      HP_NCCL(N.Recv(pb, nb, ncclDouble, t, comm, stream));
+    } else {
+      HP_NCCL(N.Send(pb, nb, ncclDouble, t, comm, stream));
+      HP_NCCL(N.Recv(pa, na, ncclDouble, t, comm, stream));
+    }
+  }
+  HP_NCCL(N.GroupEnd());
+  {  // own block never leaves the device
+    const size_t n = (size_t)ncomp * nr_loc * nm_loc * 2;
+    double* pa = A + (size_t)aoff[(size_t)rank] * 2;
+    double* pb = B + (size_t)boff[(size_t)rank] * 2;
+    HP_CUDA(cudaMemcpyAsync(synthesis ? pb : pa, synthesis ? pa : pb, n * sizeof(double),
+                            cudaMemcpyDeviceToDevice, stream));
+  }
+}
+
+void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
+  HP_REQUIRE(ncomp == 1 || ncomp == 2, HPSHT_ERR_ARG, "Number of components must be 1 (spin 0) or 2 (spin 2).");
+  HP_REQUIRE(ncomp <= max_ncomp, HPSHT_ERR_ARG, "plan was created with max_ncomp < ncomp");
+  HP_REQUIRE(in && out, HPSHT_ERR_ARG, "null data pointer");
+  HP_CUDA(cudaSetDevice(device));
+  ensure_stages();
+  leg.reset_launches();
+  fft.reset_launches();
+  int64_t extra = 0;
+  const size_t alm_d = (size_t)nalm_loc * ncomp * 2, map_d = (size_t)npix_loc * ncomp;
+  const bool in_dev = is_device_pointer(in), out_dev = is_device_pointer(out);
+  if (!tm) tm.reset(new Timer());
+  cudaEvent_t* e = tm->ev;
+  HP_CUDA(cudaEventRecord(e[0], stream));
+  const double* d_in = in;
+  double* d_out = out;
+  if (!in_dev) {
+    DevBuf<double>& sb = synthesis ? stage_alm : stage_map;
+    sb.ensure(synthesis ? alm_d : map_d);
+    HP_CUDA(cudaMemcpyAsync(sb.p, in, (synthesis ? alm_d : map_d) * sizeof(double),
+                            cudaMemcpyHostToDevice, stream));
+    d_in = sb.p;
+  }
+  if (!out_dev) {
+    DevBuf<double>& sb = synthesis ? stage_map : stage_alm;
+    sb.ensure(synthesis ? map_d : alm_d);
+    d_out = sb.p;
+  }
+  HP_CUDA(cudaEventRecord(e[1], stream));
+  const int TB = 256;
+  if (synthesis) {
+    // alm2leg (src/sht.jl:85)
+    if (P == 1) {
+      leg.alm2leg(d_in, nalm_loc, legF.p, (int64_t)max_ncomp * nr_loc * nm_tot, ncomp, stream);
+      HP_CUDA(cudaEventRecord(e[2], stream));
+      HP_CUDA(cudaEventRecord(e[3], stream));
+    } else {
+      leg.alm2leg(d_in, nalm_loc, almside.p, aoff[(size_t)P], ncomp, stream);
+      HP_CUDA(cudaEventRecord(e[2], stream));
+      exchange(true, ncomp);  // src/sht.jl:90
+      dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nr_loc));
+      k_unpack<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(mapside.p), d_boff.p,
+                                        reinterpret_cast<double2*>(legF.p), nm_tot, nr_loc, ncomp, P, lmax);
+      HP_CUDA(cudaGetLastError());
+      extra += 2;
+      HP_CUDA(cudaEventRecord(e[3], stream));
+    }
+    // leg2map (src/sht.jl:93)
+    fft.leg2map(legF.p, d_out, npix_loc, ncomp, stream);
+    HP_CUDA(cudaEventRecord(e[4], stream));
+  } else {
+    // map2leg (src/sht.jl:169)
+    fft.map2leg(d_in, npix_loc, legF.p, ncomp, stream);
+    HP_CUDA(cudaEventRecord(e[2], stream));
+    if (P == 1) {
+      HP_CUDA(cudaEventRecord(e[3], stream));
+      leg.leg2alm(legF.p, d_out, nalm_loc, ncomp, stream);  // src/sht.jl:178
+    } else {
+      dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nr_loc));
+      k_pack<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(legF.p), d_boff.p,
+                                      reinterpret_cast<double2*>(mapside.p), nm_tot, nr_loc, ncomp, P, lmax);
+      HP_CUDA(cudaGetLastError());
+      extra += 2;
+      exchange(false, ncomp);  // src/sht.jl:174
+      HP_CUDA(cudaEventRecord(e[3], stream));
+      leg.leg2alm(almside.p, d_out, nalm_loc, ncomp, stream);
+    }
+    HP_CUDA(cudaEventRecord(e[4], stream));
+  }
+  if (!out_dev)
+    HP_CUDA(cudaMemcpyAsync(out, d_out, (synthesis ? map_d : alm_d) * sizeof(double),
+                            cudaMemcpyDeviceToHost, stream));
+  HP_CUDA(cudaEventRecord(e[5], stream));
+  HP_CUDA(cudaStreamSynchronize(stream));
+  auto el = [&](int a, int b) {
+    float f = 0;
+    cudaEventElapsedTime(&f, e[a], e[b]);
+    return (double)f;
+  };
+  std::memset(ms, 0, sizeof(ms));
+  ms[0] = el(0, 5);
+  ms[5] = el(0, 1);
+  ms[6] = el(4, 5);
+  ms[3] = el(2, 3);
+  if (synthesis) {
+    ms[2] = el(1, 2);  // includes the O(nalm) prep kernel
+    ms[4] = el(3, 4);
+  } else {
+    ms[4] = el(1, 2);
+    ms[2] = el(3, 4);  // includes reduce + post kernels
+  }
+  ms[1] = leg.main_kernel_ms();
+  n_launch = leg.launches() + fft.launches() + extra;
+}
+
+// =================================================================================================
+// stage-level caches (the reference calls the four Ducc0 functions with the same descriptors over
+// and over from its solver loops; tables are rebuilt only when the descriptors change)
+// =================================================================================================
+namespace {
+
+struct LegKey {
+  int64_t lmax = -1, nm = 0, nring = 0;
+  std::vector<int64_t> mval, mstart;
+  std::vector<double> theta;
+  bool operator==(const LegKey& o) const {
+    return lmax == o.lmax && nm == o.nm && nring == o.nring && mval == o.mval && mstart == o.mstart &&
+           theta == o.theta;
+  }
+};
+struct FftKey {
+  int64_t nm = 0, nring = 0;
+  std::vector<int64_t> nphi, rstart;
+  std::vector<double> phi0;
+  bool operator==(const FftKey& o) const {
+    return nm == o.nm && nring == o.nring && nphi == o.nphi && rstart == o.rstart && phi0 == o.phi0;
+  }
+};
+struct StageCache {
+  std::mutex mu;
+  LegKey lkey;
+  std::unique_ptr<LegendreStage> leg;
+  FftKey fkey;
+  std::unique_ptr<RingFFT> fft;
+  DevBuf<double> d_alm, d_leg, d_map;
+};
+StageCache& cache() {
+  static StageCache c;
+  return c;
+}
+
+LegendreStage& get_leg_stage(StageCache& c, int64_t lmax, int64_t nm, const int64_t* mval,
+                             const int64_t* mstart, int64_t nring, const double* theta) {
+  LegKey k;
+  k.lmax = lmax;
+  k.nm = nm;
+  k.nring = nring;
+  k.mval.assign(mval, mval + nm);
+  k.mstart.assign(mstart, mstart + nm);
+  k.theta.assign(theta, theta + nring);
+  if (!c.leg || !(c.lkey == k)) {
+    c.leg.reset(new LegendreStage());
+    LegLayout lay;  // reference alm-side layout (nm, nring, ncomp): leg[(comp*nring + ir)*nm + mi]
+    lay.base.resize((size_t)nring);
+    lay.mstride.assign((size_t)nring, 1);
+    lay.cstride.assign((size_t)nring, nring * nm);
+    for (int64_t s = 0; s < nring; ++s) lay.base[(size_t)s] = s * nm;
+    c.leg->setup(lmax, mval, mstart, nm, nring, theta, lay, 2, 0);
+    c.lkey = k;
+  }
+  return *c.leg;
+}
+
+RingFFT& get_fft_stage(StageCache& c, int64_t nm, int64_t nring, const int64_t* nphi,
+                       const double* phi0, const int64_t* rstart) {
+  FftKey k;
+  k.nm = nm;
+  k.nring = nring;
+  k.nphi.assign(nphi, nphi + nring);
+  k.rstart.assign(rstart, rstart + nring);
+  k.phi0.assign(phi0, phi0 + nring);
+  if (!c.fft || !(c.fkey == k)) {
+    c.fft.reset(new RingFFT());
+    c.fft->setup(nring, nphi, phi0, rstart, nm, 0);
+    c.fkey = k;
+  }
+  return *c.fft;
+}
+
+int64_t alm_extent(int64_t lmax, int64_t nm, const int64_t* mval, const int64_t* mstart) {
+  int64_t ext = 0;
+  for (int64_t i = 0; i < nm; ++i) {
+    HP_REQUIRE(mval[i] >= 0 && mval[i] <= lmax, HPSHT_ERR_ARG, "mval out of range");
+    HP_REQUIRE(mstart[i] + mval[i] >= 0, HPSHT_ERR_ARG, "mstart points before the array");
+    ext = std::max(ext, mstart[i] + lmax + 1);
+  }
+  return ext;
+}
+
+// stage a (possibly host) input on the device; returns the device pointer to use
+const double* stage_in(const double* p, size_t n, DevBuf<double>& buf) {
+  if (is_device_pointer(p)) return p;
+  buf.ensure(n);
+  HP_CUDA(cudaMemcpy(buf.p, p, n * sizeof(double), cudaMemcpyHostToDevice));
+  return buf.p;
+}
+double* stage_out(double* p, size_t n, DevBuf<double>& buf) {
+  if (is_device_pointer(p)) return p;
+  buf.ensure(n);
+  return buf.p;
+}
+void finish_out(double* user, const double* dev, size_t n) {
+  HP_CUDA(cudaDeviceSynchronize());
+  if (user != dev) HP_CUDA(cudaMemcpy(user, dev, n * sizeof(double), cudaMemcpyDeviceToHost));
+}
+
+}  // namespace
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+extern "C" {
+
+int hpsht_version(void) { return HPSHT_VERSION_MAJOR * 100 + HPSHT_VERSION_MINOR; }
+const char* hpsht_last_error(void) { return g_last_error.c_str(); }
+int hpsht_device_count(int* count) {
+  return guarded([&] {
+    HP_REQUIRE(count, HPSHT_ERR_ARG, "null pointer");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    *count = n;
+  });
+}
+
+// ---- RR bookkeeping ----
+#define RR_CHECK(rank, size)                                                                     \
+  HP_REQUIRE((size) >= 1 && (rank) >= 0 && (rank) < (size), HPSHT_ERR_ARG,                       \
+             std::to_string(rank) + " can not exceed communicator size")
+
+int hpsht_rr_nm(int64_t mmax, int task_rank, int c_size, int64_t* nm) {
+  return guarded([&] {
+    RR_CHECK(task_rank, c_size);
+    HP_REQUIRE(nm && mmax >= 0, HPSHT_ERR_ARG, "bad argument");
+    *nm = rr_nm(mmax, task_rank, c_size);
+  });
+}
+int hpsht_rr_mval(int64_t mmax, int task_rank, int c_size, int64_t* mval) {
+  return guarded([&] {
+    RR_CHECK(task_rank, c_size);
+    HP_REQUIRE(mval && mmax >= 0, HPSHT_ERR_ARG, "bad argument");
+    std::vector<int64_t> v = rr_mval(mmax, task_rank, c_size);
+    std::copy(v.begin(), v.end(), mval);
+  });
+}
+int hpsht_rr_m_tasks(int64_t mmax, int c_size, int64_t* task) {
+  return guarded([&] {
+    HP_REQUIRE(task && mmax >= 0 && c_size >= 1, HPSHT_ERR_ARG, "bad argument");
+    for (int64_t m = 0; m <= mmax; ++m) task[m] = m % c_size;
+  });
+}
+int hpsht_rr_mstart(int64_t lmax, int64_t stride, int64_t nm, const int64_t* mval, int64_t* mstart) {
+  return guarded([&] {
+    HP_REQUIRE(mval && mstart && nm >= 0, HPSHT_ERR_ARG, "bad argument");
+    std::vector<int64_t> mv(mval, mval + nm);
+    std::vector<int64_t> v = rr_mstart0(lmax, stride, mv);
+    std::copy(v.begin(), v.end(), mstart);
+  });
+}
+int hpsht_rr_nrings(int64_t eq_idx, int task_rank, int c_size, int64_t* nrings) {
+  return guarded([&] {
+    RR_CHECK(task_rank, c_size);
+    HP_REQUIRE(nrings && eq_idx >= 1, HPSHT_ERR_ARG, "bad argument");
+    *nrings = rr_nrings(eq_idx, task_rank, c_size);
+  });
+}
+int hpsht_rr_rindexes(int64_t eq_idx, int task_rank, int c_size, int64_t* rings) {
+  return guarded([&] {
+    RR_CHECK(task_rank, c_size);
+    HP_REQUIRE(rings && eq_idx >= 1, HPSHT_ERR_ARG, "bad argument");
+    std::vector<int64_t> v = rr_rindexes(eq_idx, task_rank, c_size);
+    std::copy(v.begin(), v.end(), rings);
+  });
+}
+int hpsht_rr_rindexes_tot(int64_t eq_idx, int c_size, int64_t* rings) {
+  return guarded([&] {
+    HP_REQUIRE(rings && eq_idx >= 1 && c_size >= 1, HPSHT_ERR_ARG, "bad argument");
+    std::vector<int64_t> v = rr_rindexes_tot(eq_idx, c_size);
+    std::copy(v.begin(), v.end(), rings);
+  });
+}
+int hpsht_rr_a2a_counts(int64_t mmax, int64_t eq_idx, int task_rank, int c_size, int64_t* send,
+                        int64_t* recv) {
+  return guarded([&] {
+    RR_CHECK(task_rank, c_size);
+    HP_REQUIRE(send && recv, HPSHT_ERR_ARG, "bad argument");
+    const int64_t loc_nm = rr_nm(mmax, task_rank, c_size), loc_nr = rr_nrings(eq_idx, task_rank, c_size);
+    for (int t = 0; t < c_size; ++t) {
+      send[t] = loc_nm * rr_nrings(eq_idx, t, c_size);
+      recv[t] = loc_nr * rr_nm(mmax, t, c_size);
+    }
+  });
+}
+int hpsht_healpix_ring(int64_t nside, int64_t ring, int64_t* nphi, double* theta, double* phi0,
+                       int64_t* first_pix) {
+  return guarded([&] {
+    HP_REQUIRE(nside >= 1 && ring >= 1 && ring <= 4 * nside - 1, HPSHT_ERR_ARG, "ring out of range");
+    RingGeom g = healpix_ring(nside, ring);
+    if (nphi) *nphi = g.nphi;
+    if (theta) *theta = g.theta;
+    if (phi0) *phi0 = g.phi0;
+    if (first_pix) *first_pix = g.first_pix;
+  });
+}
+
+// ---- stage level ----
+int hpsht_alm2leg(const double* alm, int64_t alm_cstride, double* leg, int spin, int64_t lmax,
+                  int64_t nm, const int64_t* mval, const int64_t* mstart, int64_t lstride,
+                  int64_t nring, const double* theta, int /*nthreads*/) {
+  return guarded([&] {
+    HP_REQUIRE(spin == 0 || spin == 2, HPSHT_ERR_UNSUPPORTED, "only spin 0 and spin 2 are supported");
+    HP_REQUIRE(lstride == 1, HPSHT_ERR_UNSUPPORTED, "lstride must be 1");
+    HP_REQUIRE(alm && leg && mval && mstart && theta && nm > 0 && nring > 0 && lmax >= 0,
+               HPSHT_ERR_ARG, "bad argument");
+    require_device();
+    const int ncomp = spin == 0 ? 1 : 2;
+    const int64_t ext = alm_extent(lmax, nm, mval, mstart);
+    HP_REQUIRE(ncomp == 1 || alm_cstride >= ext, HPSHT_ERR_ARG, "alm_cstride too small");
+    StageCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    LegendreStage& st = get_leg_stage(c, lmax, nm, mval, mstart, nring, theta);
+    const size_t nalm = (size_t)(ncomp == 1 ? ext : alm_cstride + ext) * 2;
+    const size_t nleg = (size_t)ncomp * nring * nm * 2;
+    const double* d_alm = stage_in(alm, nalm, c.d_alm);
+    double* d_leg = stage_out(leg, nleg, c.d_leg);
+    st.alm2leg(d_alm, alm_cstride, d_leg, (int64_t)ncomp * nring * nm, ncomp, 0);
+    finish_out(leg, d_leg, nleg);
+  });
+}
+
+int hpsht_leg2alm(const double* leg, double* alm, int64_t alm_cstride, int spin, int64_t lmax,
+                  int64_t nm, const int64_t* mval, const int64_t* mstart, int64_t lstride,
+                  int64_t nring, const double* theta, int /*nthreads*/) {
+  return guarded([&] {
+    HP_REQUIRE(spin == 0 || spin == 2, HPSHT_ERR_UNSUPPORTED, "only spin 0 and spin 2 are supported");
+    HP_REQUIRE(lstride == 1, HPSHT_ERR_UNSUPPORTED, "lstride must be 1");
+    HP_REQUIRE(alm && leg && mval && mstart && theta && nm > 0 && nring > 0 && lmax >= 0,
+               HPSHT_ERR_ARG, "bad argument");
+    require_device();
+    const int ncomp = spin == 0 ? 1 : 2;
+    const int64_t ext = alm_extent(lmax, nm, mval, mstart);
+    HP_REQUIRE(ncomp == 1 || alm_cstride >= ext, HPSHT_ERR_ARG, "alm_cstride too small");
+    StageCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    LegendreStage& st = get_leg_stage(c, lmax, nm, mval, mstart, nring, theta);
+    const size_t nalm = (size_t)(ncomp == 1 ? ext : alm_cstride + ext) * 2;
+    const size_t nleg = (size_t)ncomp * nring * nm * 2;
+    const double* d_leg = stage_in(leg, nleg, c.d_leg);
+    const bool host_out = !is_device_pointer(alm);
+    double* d_alm = stage_out(alm, nalm, c.d_alm);
+    // entries of the caller's array that are not a_lm of an owned m must survive untouched
+    if (host_out) HP_CUDA(cudaMemcpy(d_alm, alm, nalm * sizeof(double), cudaMemcpyHostToDevice));
+    st.leg2alm(d_leg, d_alm, alm_cstride, ncomp, 0);
+    finish_out(alm, d_alm, nalm);
+  });
+}
+
+int hpsht_leg2map(const double* leg, double* map, int64_t map_cstride, int ncomp, int64_t nm,
+                  int64_t nring, const int64_t* nphi, const double* phi0, const int64_t* ringstart,
+                  int64_t pixstride, int /*nthreads*/) {
+  return guarded([&] {
+    HP_REQUIRE(pixstride == 1, HPSHT_ERR_UNSUPPORTED, "pixstride must be 1");
+    HP_REQUIRE(ncomp == 1 || ncomp == 2, HPSHT_ERR_ARG, "ncomp must be 1 or 2");
+    HP_REQUIRE(leg && map && nphi && phi0 && ringstart && nm > 0 && nring > 0, HPSHT_ERR_ARG,
+               "bad argument");
+    require_device();
+    int64_t ext = 0;
+    for (int64_t i = 0; i < nring; ++i) {
+      HP_REQUIRE(ringstart[i] >= 0, HPSHT_ERR_ARG, "negative ringstart");
+      ext = std::max(ext, ringstart[i] + nphi[i]);
+    }
+    HP_REQUIRE(ncomp == 1 || map_cstride >= ext, HPSHT_ERR_ARG, "map_cstride too small");
+    StageCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    RingFFT& f = get_fft_stage(c, nm, nring, nphi, phi0, ringstart);
+    const size_t nleg = (size_t)ncomp * nring * nm * 2;
+    const size_t nmap = (size_t)(ncomp == 1 ? ext : map_cstride + ext);
+    const double* d_leg = stage_in(leg, nleg, c.d_leg);
+    const bool host_out = !is_device_pointer(map);
+    double* d_map = stage_out(map, nmap, c.d_map);
+    if (host_out) HP_CUDA(cudaMemcpy(d_map, map, nmap * sizeof(double), cudaMemcpyHostToDevice));
+    f.leg2map(d_leg, d_map, map_cstride, ncomp, 0);
+    finish_out(map, d_map, nmap);
+  });
+}
+
+int hpsht_map2leg(const double* map, int64_t map_cstride, double* leg, int ncomp, int64_t nm,
+                  int64_t nring, const int64_t* nphi, const double* phi0, const int64_t* ringstart,
+                  int64_t pixstride, int /*nthreads*/) {
+  return guarded([&] {
+    HP_REQUIRE(pixstride == 1, HPSHT_ERR_UNSUPPORTED, "pixstride must be 1");
+    HP_REQUIRE(ncomp == 1 || ncomp == 2, HPSHT_ERR_ARG, "ncomp must be 1 or 2");
+    HP_REQUIRE(leg && map && nphi && phi0 && ringstart && nm > 0 && nring > 0, HPSHT_ERR_ARG,
+               "bad argument");
+    require_device();
+    int64_t ext = 0;
+    for (int64_t i = 0; i < nring; ++i) {
+      HP_REQUIRE(ringstart[i] >= 0, HPSHT_ERR_ARG, "negative ringstart");
+      ext = std::max(ext, ringstart[i] + nphi[i]);
+    }
+    HP_REQUIRE(ncomp == 1 || map_cstride >= ext, HPSHT_ERR_ARG, "map_cstride too small");
+    StageCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    RingFFT& f = get_fft_stage(c, nm, nring, nphi, phi0, ringstart);
+    const size_t nleg = (size_t)ncomp * nring * nm * 2;
+    const size_t nmap = (size_t)(ncomp == 1 ? ext : map_cstride + ext);
+    const double* d_map = stage_in(map, nmap, c.d_map);
+    double* d_leg = stage_out(leg, nleg, c.d_leg);
+    f.map2leg(d_map, map_cstride, d_leg, ncomp, 0);
+    finish_out(leg, d_leg, nleg);
+  });
+}
+
+// ---- fused plan ----
+int hpsht_nccl_unique_id(unsigned char id[HPSHT_NCCL_ID_BYTES]) {
+  return guarded([&] {
+    HP_REQUIRE(id, HPSHT_ERR_ARG, "null pointer");
+    static_assert(sizeof(ncclUniqueId) == HPSHT_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId u;
+    HP_NCCL(NcclApi::get().GetUniqueId(&u));
+    std::memcpy(id, &u, sizeof(u));
+  });
+}
+
+int hpsht_plan_create(hpsht_plan** plan, int64_t nside, int64_t lmax, int rank, int n_ranks,
+                      const unsigned char* nccl_id, int device, int max_ncomp) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan pointer");
+    *plan = nullptr;
+    HP_REQUIRE(n_ranks >= 1, HPSHT_ERR_ARG, "n_ranks must be >= 1");
+    HP_REQUIRE(max_ncomp == 1 || max_ncomp == 2, HPSHT_ERR_ARG, "max_ncomp must be 1 or 2");
+    HP_REQUIRE(n_ranks == 1 || nccl_id, HPSHT_ERR_ARG, "nccl_id required when n_ranks > 1");
+    std::unique_ptr<hpsht_plan> p(new hpsht_plan());
+    p->nside = nside;
+    p->lmax = lmax;
+    p->rank = rank;
+    p->P = n_ranks;
+    p->max_ncomp = max_ncomp;
+    p->build_shard();  // pure host work: argument errors surface before any CUDA call
+    require_device();
+    if (device < 0) HP_CUDA(cudaGetDevice(&device));
+    p->device = device;
+    HP_CUDA(cudaSetDevice(device));
+    HP_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    if (n_ranks > 1) {
+      ncclUniqueId u;
+      std::memcpy(&u, nccl_id, sizeof(u));
+      HP_NCCL(NcclApi::get().CommInitRank(&p->comm, n_ranks, u, rank));
+    }
+    *plan = p.release();
+  });
+}
+
+int hpsht_plan_set_geometry(hpsht_plan* plan, const double* thetatot, const double* phi0_loc) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    HP_REQUIRE(!plan->stages_ready, HPSHT_ERR_ARG, "geometry must be set before the first transform");
+    if (thetatot) plan->thetatot.assign(thetatot, thetatot + plan->nr_tot);
+    if (phi0_loc) plan->phi0.assign(phi0_loc, phi0_loc + plan->nr_loc);
+  });
+}
+
+int hpsht_plan_destroy(hpsht_plan* plan) {
+  return guarded([&] {
+    if (!plan) return;
+    cudaSetDevice(plan->device);
+    if (plan->stream) cudaStreamSynchronize(plan->stream);
+    if (plan->comm) NcclApi::get().CommDestroy(plan->comm);
+    if (plan->stream) cudaStreamDestroy(plan->stream);
+    delete plan;
+  });
+}
+
+int hpsht_plan_sizes(const hpsht_plan* plan, int64_t* nm_loc, int64_t* nalm_loc, int64_t* nring_loc,
+                     int64_t* npix_loc, int64_t* nring_tot) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    if (nm_loc) *nm_loc = plan->nm_loc;
+    if (nalm_loc) *nalm_loc = plan->nalm_loc;
+    if (nring_loc) *nring_loc = plan->nr_loc;
+    if (npix_loc) *npix_loc = plan->npix_loc;
+    if (nring_tot) *nring_tot = plan->nr_tot;
+  });
+}
+int hpsht_plan_alm_info(const hpsht_plan* plan, int64_t* mval, int64_t* mstart) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    if (mval) std::copy(plan->mval.begin(), plan->mval.end(), mval);
+    if (mstart) std::copy(plan->mstart.begin(), plan->mstart.end(), mstart);
+  });
+}
+int hpsht_plan_map_info(const hpsht_plan* plan, int64_t* rings, int64_t* rstart, int64_t* nphi,
+                        double* theta, double* phi0, double* thetatot) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    if (rings) std::copy(plan->rings.begin(), plan->rings.end(), rings);
+    if (rstart) std::copy(plan->rstart.begin(), plan->rstart.end(), rstart);
+    if (nphi) std::copy(plan->nphi.begin(), plan->nphi.end(), nphi);
+    if (theta) std::copy(plan->theta.begin(), plan->theta.end(), theta);
+    if (phi0) std::copy(plan->phi0.begin(), plan->phi0.end(), phi0);
+    if (thetatot) std::copy(plan->thetatot.begin(), plan->thetatot.end(), thetatot);
+  });
+}
+
+int hpsht_alm2map(hpsht_plan* plan, const double* alm, double* map, int ncomp, int /*nthreads*/) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    plan->run(true, alm, map, ncomp);
+  });
+}
+int hpsht_adjoint_alm2map(hpsht_plan* plan, const double* map, double* alm, int ncomp,
+                          int /*nthreads*/) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    plan->run(false, map, alm, ncomp);
+  });
+}
+
+int hpsht_plan_timings(const hpsht_plan* plan, double ms[HPSHT_NTIMES]) {
+  return guarded([&] {
+    HP_REQUIRE(plan && ms, HPSHT_ERR_ARG, "null pointer");
+    std::memcpy(ms, plan->ms, sizeof(plan->ms));
+  });
+}
+int hpsht_plan_launches(const hpsht_plan* plan, int64_t* n) {
+  return guarded([&] {
+    HP_REQUIRE(plan && n, HPSHT_ERR_ARG, "null pointer");
+    *n = plan->n_launch;
+  });
+}
+int hpsht_plan_legendre_steps(const hpsht_plan* plan, int spin, double* steps_culled,
+                              double* steps_dense) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    // pure host arithmetic on the shard description (no device needed)
+    std::vector<PairHost> pairs = build_pairs(plan->lmax, plan->nr_tot, plan->thetatot.data());
+    double c = 0, d = 0;
+    for (const PairHost& p : pairs)
+      for (int64_t m : plan->mval) {
+        const double w = (double)(plan->lmax - m + 1);
+        d += w;
+        if (m <= (spin ? p.mlim2 : p.mlim0)) c += w;
+      }
+    if (steps_culled) *steps_culled = c;
+    if (steps_dense) *steps_dense = d;
+  });
+}
+
+// ---- device memory helpers ----
+int hpsht_device_malloc(void** dptr, size_t bytes) {
+  return guarded([&] {
+    HP_REQUIRE(dptr, HPSHT_ERR_ARG, "null pointer");
+    require_device();
+    HP_CUDA(cudaMalloc(dptr, bytes));
+  });
+}
+int hpsht_device_free(void* dptr) {
+  return guarded([&] { HP_CUDA(cudaFree(dptr)); });
+}
+int hpsht_host_malloc(void** hptr, size_t bytes) {
+  return guarded([&] {
+    HP_REQUIRE(hptr, HPSHT_ERR_ARG, "null pointer");
+    require_device();
+    HP_CUDA(cudaMallocHost(hptr, bytes));
+  });
+}
+int hpsht_host_free(void* hptr) {
+  return guarded([&] { HP_CUDA(cudaFreeHost(hptr)); });
+}
+int hpsht_memcpy_h2d(void* dptr, const void* hptr, size_t bytes) {
+  return guarded([&] { HP_CUDA(cudaMemcpy(dptr, hptr, bytes, cudaMemcpyHostToDevice)); });
+}
+int hpsht_memcpy_d2h(void* hptr, const void* dptr, size_t bytes) {
+  return guarded([&] { HP_CUDA(cudaMemcpy(hptr, dptr, bytes, cudaMemcpyDeviceToHost)); });
+}
+int hpsht_device_synchronize(void) {
+  return guarded([&] { HP_CUDA(cudaDeviceSynchronize()); });
+}
+
+int hpsht_measure_fp64_peak(double* tflops, double* seconds_run) {
+  return guarded([&] {
+    HP_REQUIRE(tflops, HPSHT_ERR_ARG, "null pointer");
+    require_device();
+    cudaDeviceProp prop;
+    int dev = 0;
+    HP_CUDA(cudaGetDevice(&dev));
+    HP_CUDA(cudaGetDeviceProperties(&prop, dev));
+    DevBuf<double> out;
+    out.alloc(1);
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 20000;
+    cudaEvent_t a, b;
+    HP_CUDA(cudaEventCreate(&a));
+    HP_CUDA(cudaEventCreate(&b));
+    k_dfma_peak<<<blocks, threads>>>(out.p, 200, 0.5);  // warm-up
+    double best = 0, total = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+      HP_CUDA(cudaEventRecord(a));
+      k_dfma_peak<<<blocks, threads>>>(out.p, iters, 0.5);
+      HP_CUDA(cudaEventRecord(b));
+      HP_CUDA(cudaEventSynchronize(b));
+      float msf = 0;
+      HP_CUDA(cudaEventElapsedTime(&msf, a, b));
+      const double flop = 2.0 * 64.0 * (double)iters * threads * (double)blocks;
+      best = std::max(best, flop / (msf * 1e-3) / 1e12);
+      total += msf * 1e-3;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
+    if (seconds_run) *seconds_run = total;
+  });
+}
+
+}  // extern "C"

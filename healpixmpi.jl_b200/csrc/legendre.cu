@@ -1,0 +1,1447 @@
+// legendre.cu — sm_100a FP64 kernels of the Legendre stage: alm2leg / leg2alm, spin 0 and spin 2.
+//
+// Replaces Ducc0.Sht.alm2leg! (reference src/sht.jl:85) and Ducc0.Sht.leg2alm! (src/sht.jl:178).
+//
+// Kernel design (B200-first):
+//   * one CTA = one work item = (one local m) x (one tile of N/S ring pairs, sorted pole->equator);
+//   * every consumer thread owns R ring pairs and evaluates the scaled recurrence on the fly in
+//     registers (no Plm table); north/south symmetry gives both rings of a pair from one recurrence;
+//   * the per-m coefficient stream (recurrence coefficients + prepared alm) is the only data the
+//     inner loop reads; a dedicated producer warp moves it global->shared with 1-D TMA bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx) through a 4-stage full/empty mbarrier ring, and the
+//     consumers read it as warp-broadcast LDS.128;
+//   * dynamic range: value = lam * 2^(800*sc), sc <= 0 tracked per ring; a warp whose lanes are all
+//     still below range runs a 2-FMA "ramp" step instead of the full 6-FMA (spin 0) / 12-FMA
+//     (spin 2) step; range checks every 8 steps;
+//   * adjoint: per-thread accumulation over its R rings, transposed-butterfly warp-shuffle reduction
+//     over the 32 lanes every 4 steps, cross-warp reduction through shared memory once per 64-step
+//     chunk, deterministic per-tile partial sums in global memory (no atomics).
+#include "legendre.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace hpsht {
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int NSTAGE = 4;
+constexpr double SC_BIG = 2.5822498780869086e+120;      // 2^400
+constexpr double SC_DOWN = 1.4997597826618576e-241;     // 2^-800
+constexpr int SC_STEP = 800;
+
+struct __align__(16) Coef {
+  double a, b;
+};
+struct __align__(16) Strm {
+  double x, y, z, w;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// base^n (n >= 0) as mant * 2^e, mant in [0.5, 1)
+__device__ __forceinline__ void pow_scaled(double base, int n, double& mant, int& e) {
+  int be;
+  double b = frexp(base, &be);
+  mant = 1.0;
+  e = 0;
+  while (n > 0) {
+    if (n & 1) {
+      mant *= b;
+      e += be;
+      int t;
+      mant = frexp(mant, &t);
+      e += t;
+    }
+    b *= b;
+    be *= 2;
+    int t;
+    b = frexp(b, &t);
+    be += t;
+    n >>= 1;
+  }
+}
+// v * 2^e -> lam * 2^(800 sc), sc <= 0, |lam| in [2^-400, 2^400) when sc < 0
+__device__ __forceinline__ void to_scaled(double v, int e, double& lam, int& sc) {
+  if (v == 0.0) {
+    lam = 0.0;
+    sc = 0;
+    return;
+  }
+  int t;
+  v = frexp(v, &t);
+  e += t;
+  sc = (e >= -400) ? 0 : -((-e - 400 + SC_STEP - 1) / SC_STEP);
+  int ee = e - SC_STEP * sc;
+  lam = (ee < -1070) ? 0.0 : ldexp(v, ee);
+}
+__device__ __forceinline__ bool is_big(double v) {
+  // |v| > 2^400  <=>  biased exponent field > 1023+400 (ties at exactly 2^400 are irrelevant)
+  return ((__double2hiint(v) >> 20) & 0x7ff) > 1023 + 400;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameter block
+// ------------------------------------------------------------------------------------------------
+struct LegParams {
+  const WorkItem* items;
+  // per local m
+  const int64_t* mval;
+  const int64_t* nstep;   // real steps
+  const int64_t* off;     // table offset in steps (padded to LEG_CHUNK)
+  const double* coef;     // 2 doubles / step
+  const double* k0;       // spin0: p_0 constant ; spin2: kp2
+  const double* k1;       // spin2: km2
+  // per pair
+  const double* cth;
+  const double* sth;
+  const double* sh;
+  const double* ch;
+  const int* mlim;
+  const int64_t* offN;
+  const int64_t* offS;
+  const int64_t* mstr;
+  const int64_t* cstr;
+  // data
+  const double* stream;   // 4 doubles / step (synthesis input)
+  double* leg;            // complex128 (synthesis out / adjoint in)
+  double* part;           // adjoint partial sums, 4 doubles / step
+  const int64_t* partoff; // per item: offset in steps into part
+};
+
+// ------------------------------------------------------------------------------------------------
+// producer warp: streams `nchunks` chunks of coef (and optionally the alm stream) into the ring
+// ------------------------------------------------------------------------------------------------
+template <bool WITH_STREAM>
+__device__ __forceinline__ void producer_loop(int nchunks, int nrepeat, const double* gcoef,
+                                              const double* gstrm, Coef (*s_coef)[LEG_CHUNK],
+                                              Strm (*s_strm)[LEG_CHUNK], uint64_t* full,
+                                              uint64_t* empty) {
+  int cg = 0;  // position in the stage ring (the same stream is replayed once per tile)
+  for (int rep = 0; rep < nrepeat; ++rep) {
+    for (int c = 0; c < nchunks; ++c, ++cg) {
+      const int st = cg % NSTAGE;
+      if (cg >= NSTAGE) mbar_wait(&empty[st], ((cg / NSTAGE) - 1) & 1);
+      const uint32_t bytes = LEG_CHUNK * sizeof(Coef) + (WITH_STREAM ? LEG_CHUNK * sizeof(Strm) : 0);
+      mbar_arrive_expect_tx(&full[st], bytes);
+      tma_load_1d(&s_coef[st][0], gcoef + (size_t)c * LEG_CHUNK * 2, LEG_CHUNK * sizeof(Coef),
+                  &full[st]);
+      if (WITH_STREAM)
+        tma_load_1d(&s_strm[st][0], gstrm + (size_t)c * LEG_CHUNK * 4, LEG_CHUNK * sizeof(Strm),
+                    &full[st]);
+    }
+  }
+}
+
+// ================================================================================================
+// spin 0 synthesis:  leg_N/S = sum_n p_n A_n  +-  x sum_n p_n B_n
+// ================================================================================================
+template <int R, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
+  __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
+  __shared__ Strm s_strm[NSTAGE][LEG_CHUNK];
+  __shared__ __align__(8) uint64_t s_full[NSTAGE];
+  __shared__ __align__(8) uint64_t s_empty[NSTAGE];
+
+  const WorkItem it = P.items[blockIdx.x];
+  const int mi = it.mi;
+  const int m = (int)P.mval[mi];
+  const int nn = (int)P.nstep[mi];
+  const int nsteps = (nn + LEG_GROUP - 1) / LEG_GROUP * LEG_GROUP;
+  const int nchunks = (nsteps + LEG_CHUNK - 1) / LEG_CHUNK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {  // ---------------- producer warp ----------------
+    if (lane == 0)
+      producer_loop<true>(nchunks, 1, P.coef + (size_t)P.off[mi] * 2, P.stream + (size_t)P.off[mi] * 4,
+                          s_coef, s_strm, s_full, s_empty);
+    return;
+  }
+
+  // ---------------- consumer warps ----------------
+  double csq[R], lam1[R], lam2[R];
+  double er[R], ei[R], orr[R], oi[R];
+  int sc[R];
+  bool act[R];
+  bool any_act = false;
+  const double k0 = P.k0[mi];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int pl = warp * 32 * R + r * 32 + lane;
+    const bool valid = pl < it.np;
+    const int p = it.p0 + (valid ? pl : 0);
+    act[r] = valid && (m <= P.mlim[p]);
+    any_act |= act[r];
+    const double c = P.cth[p];
+    csq[r] = c * c;
+    double mant;
+    int e;
+    pow_scaled(P.sth[p], m, mant, e);
+    to_scaled(k0 * mant, e, lam2[r], sc[r]);
+    if (!act[r]) {  // culled lanes carry zeros so nothing can overflow
+      lam2[r] = 0.0;
+      sc[r] = 0;
+    }
+    lam1[r] = 0.0;
+    er[r] = ei[r] = orr[r] = oi[r] = 0.0;
+  }
+  const bool warp_act = __any_sync(0xffffffffu, any_act);
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % NSTAGE;
+    mbar_wait(&s_full[st], (c / NSTAGE) & 1);
+    if (warp_act) {
+      const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
+      for (int g = 0; g < ng; ++g) {
+        bool mine0 = false, mineneg = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          mine0 |= act[r] && (sc[r] == 0);
+          mineneg |= (sc[r] < 0);
+        }
+        const bool any0 = __any_sync(0xffffffffu, mine0);
+        const Coef* cf = &s_coef[st][g * LEG_GROUP];
+        if (any0) {
+          const Strm* sm = &s_strm[st][g * LEG_GROUP];
+#pragma unroll
+          for (int s = 0; s < LEG_GROUP; ++s) {
+            const Coef ab = cf[s];
+            const Strm al = sm[s];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              er[r] = fma(lam2[r], al.x, er[r]);
+              ei[r] = fma(lam2[r], al.y, ei[r]);
+              orr[r] = fma(lam2[r], al.z, orr[r]);
+              oi[r] = fma(lam2[r], al.w, oi[r]);
+              const double t = fma(ab.a, csq[r], ab.b);
+              const double nx = fma(t, lam2[r], lam1[r]);
+              lam1[r] = lam2[r];
+              lam2[r] = nx;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < LEG_GROUP; ++s) {
+            const Coef ab = cf[s];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const double t = fma(ab.a, csq[r], ab.b);
+              const double nx = fma(t, lam2[r], lam1[r]);
+              lam1[r] = lam2[r];
+              lam2[r] = nx;
+            }
+          }
+        }
+        if (__any_sync(0xffffffffu, mineneg)) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (sc[r] < 0 && is_big(lam2[r])) {
+              lam1[r] *= SC_DOWN;
+              lam2[r] *= SC_DOWN;
+              sc[r] += 1;
+              er[r] = ei[r] = orr[r] = oi[r] = 0.0;  // drop what was accumulated while scaled
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[st]);
+  }
+
+  // ---------------- epilogue ----------------
+  double2* leg = reinterpret_cast<double2*>(P.leg);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int pl = warp * 32 * R + r * 32 + lane;
+    if (pl >= it.np) continue;
+    const int p = it.p0 + pl;
+    const bool on = act[r] && sc[r] == 0;
+    const double c = P.cth[p];
+    const double Er = on ? er[r] : 0.0, Ei = on ? ei[r] : 0.0;
+    const double Or = on ? orr[r] * c : 0.0, Oi = on ? oi[r] * c : 0.0;
+    const int64_t rowoff = (int64_t)mi * P.mstr[p];
+    leg[P.offN[p] + rowoff] = make_double2(Er + Or, Ei + Oi);
+    const int64_t oS = P.offS[p];
+    if (oS >= 0) leg[oS + rowoff] = make_double2(Er - Or, Ei - Oi);
+  }
+}
+
+// ================================================================================================
+// spin 2 synthesis.  Stream per l: alpha+ = -(E+iB) sigma_l/2, alpha- = -(E-iB) sigma_l/2.
+//   P+N = sum alpha+ d+ ; P-N = sum alpha- d- ; P+S = sum (-1)^(l+m) alpha+ d- ; P-S = sum (-1)^(l+m) alpha- d+
+//   Q = P+ + P- ; U = -i (P+ - P-)
+// ================================================================================================
+template <int R, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
+  __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
+  __shared__ Strm s_strm[NSTAGE][LEG_CHUNK];
+  __shared__ __align__(8) uint64_t s_full[NSTAGE];
+  __shared__ __align__(8) uint64_t s_empty[NSTAGE];
+
+  const WorkItem it = P.items[blockIdx.x];
+  const int mi = it.mi;
+  const int m = (int)P.mval[mi];
+  const int nl = (int)P.nstep[mi];
+  const int nsteps = (nl + LEG_GROUP - 1) / LEG_GROUP * LEG_GROUP;
+  const int nchunks = (nsteps + LEG_CHUNK - 1) / LEG_CHUNK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    if (lane == 0)
+      producer_loop<true>(nchunks, 1, P.coef + (size_t)P.off[mi] * 2, P.stream + (size_t)P.off[mi] * 4,
+                          s_coef, s_strm, s_full, s_empty);
+    return;
+  }
+
+  double x[R], lp1[R], lp2[R], lm1[R], lm2[R];
+  double pnr[R], pni[R], mnr[R], mni[R];  // P+N, P-N
+  double psr[R], psi[R], msr[R], msi[R];  // P+S, P-S
+  int scp[R], scm[R];
+  bool act[R];
+  bool any_act = false;
+  const double kp = P.k0[mi], km = P.k1[mi];
+  const int pw = m >= 2 ? m - 2 : 2 - m;
+  const int q = m < 2 ? m : 2;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int pl = warp * 32 * R + r * 32 + lane;
+    const bool valid = pl < it.np;
+    const int p = it.p0 + (valid ? pl : 0);
+    act[r] = valid && (m <= P.mlim[p]);
+    any_act |= act[r];
+    x[r] = P.cth[p];
+    double mant;
+    int e;
+    pow_scaled(P.sth[p], pw, mant, e);
+    double fs = 1.0, fc = 1.0;
+    const double s2 = P.sh[p] * P.sh[p], c2 = P.ch[p] * P.ch[p];
+    for (int k = 0; k < q; ++k) {
+      fs *= s2;
+      fc *= c2;
+    }
+    to_scaled(kp * mant * fs, e, lp2[r], scp[r]);
+    to_scaled(km * mant * fc, e, lm2[r], scm[r]);
+    if (!act[r]) {
+      lp2[r] = lm2[r] = 0.0;
+      scp[r] = scm[r] = 0;
+    }
+    lp1[r] = lm1[r] = 0.0;
+    pnr[r] = pni[r] = mnr[r] = mni[r] = 0.0;
+    psr[r] = psi[r] = msr[r] = msi[r] = 0.0;
+  }
+  const bool warp_act = __any_sync(0xffffffffu, any_act);
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % NSTAGE;
+    mbar_wait(&s_full[st], (c / NSTAGE) & 1);
+    if (warp_act) {
+      const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
+      for (int g = 0; g < ng; ++g) {
+        bool mine0 = false, mineneg = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          mine0 |= act[r] && ((scp[r] == 0) || (scm[r] == 0));
+          mineneg |= (scp[r] < 0) || (scm[r] < 0);
+        }
+        const bool any0 = __any_sync(0xffffffffu, mine0);
+        const Coef* cf = &s_coef[st][g * LEG_GROUP];
+        if (any0) {
+          const Strm* sm = &s_strm[st][g * LEG_GROUP];
+#pragma unroll
+          for (int s = 0; s < LEG_GROUP; ++s) {
+            const Coef ab = cf[s];
+            const Strm al = sm[s];  // x,y = alpha+ ; z,w = alpha-
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              pnr[r] = fma(lp2[r], al.x, pnr[r]);
+              pni[r] = fma(lp2[r], al.y, pni[r]);
+              mnr[r] = fma(lm2[r], al.z, mnr[r]);
+              mni[r] = fma(lm2[r], al.w, mni[r]);
+              if ((s & 1) == 0) {  // steps within a group start at an even offset
+                psr[r] = fma(lm2[r], al.x, psr[r]);
+                psi[r] = fma(lm2[r], al.y, psi[r]);
+                msr[r] = fma(lp2[r], al.z, msr[r]);
+                msi[r] = fma(lp2[r], al.w, msi[r]);
+              } else {
+                psr[r] = fma(-lm2[r], al.x, psr[r]);
+                psi[r] = fma(-lm2[r], al.y, psi[r]);
+                msr[r] = fma(-lp2[r], al.z, msr[r]);
+                msi[r] = fma(-lp2[r], al.w, msi[r]);
+              }
+              const double tp = fma(x[r], ab.a, ab.b);
+              const double tm = fma(x[r], ab.a, -ab.b);
+              const double np_ = fma(tp, lp2[r], -lp1[r]);
+              const double nm_ = fma(tm, lm2[r], -lm1[r]);
+              lp1[r] = lp2[r];
+              lp2[r] = np_;
+              lm1[r] = lm2[r];
+              lm2[r] = nm_;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < LEG_GROUP; ++s) {
+            const Coef ab = cf[s];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const double tp = fma(x[r], ab.a, ab.b);
+              const double tm = fma(x[r], ab.a, -ab.b);
+              const double np_ = fma(tp, lp2[r], -lp1[r]);
+              const double nm_ = fma(tm, lm2[r], -lm1[r]);
+              lp1[r] = lp2[r];
+              lp2[r] = np_;
+              lm1[r] = lm2[r];
+              lm2[r] = nm_;
+            }
+          }
+        }
+        if (__any_sync(0xffffffffu, mineneg)) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (scp[r] < 0 && is_big(lp2[r])) {
+              lp1[r] *= SC_DOWN;
+              lp2[r] *= SC_DOWN;
+              scp[r] += 1;
+              pnr[r] = pni[r] = msr[r] = msi[r] = 0.0;
+            }
+            if (scm[r] < 0 && is_big(lm2[r])) {
+              lm1[r] *= SC_DOWN;
+              lm2[r] *= SC_DOWN;
+              scm[r] += 1;
+              mnr[r] = mni[r] = psr[r] = psi[r] = 0.0;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[st]);
+  }
+
+  double2* leg = reinterpret_cast<double2*>(P.leg);
+  const int l0 = m > 2 ? m : 2;
+  const double sgnS = ((l0 + m) & 1) ? -1.0 : 1.0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int pl = warp * 32 * R + r * 32 + lane;
+    if (pl >= it.np) continue;
+    const int p = it.p0 + pl;
+    const bool onp = act[r] && scp[r] == 0, onm = act[r] && scm[r] == 0;
+    const double PNr = onp ? pnr[r] : 0.0, PNi = onp ? pni[r] : 0.0;
+    const double MSr = onp ? msr[r] * sgnS : 0.0, MSi = onp ? msi[r] * sgnS : 0.0;
+    const double MNr = onm ? mnr[r] : 0.0, MNi = onm ? mni[r] : 0.0;
+    const double PSr = onm ? psr[r] * sgnS : 0.0, PSi = onm ? psi[r] * sgnS : 0.0;
+    const int64_t rowoff = (int64_t)mi * P.mstr[p];
+    const int64_t cs = P.cstr[p];
+    const int64_t oN = P.offN[p] + rowoff;
+    // Q = P+ + P- ; U = -i (P+ - P-) = ( Im(P+ - P-), -Re(P+ - P-) )
+    leg[oN] = make_double2(PNr + MNr, PNi + MNi);
+    leg[oN + cs] = make_double2(PNi - MNi, -(PNr - MNr));
+    const int64_t oS0 = P.offS[p];
+    if (oS0 >= 0) {
+      const int64_t oS = oS0 + rowoff;
+      leg[oS] = make_double2(PSr + MSr, PSi + MSi);
+      leg[oS + cs] = make_double2(PSi - MSi, -(PSr - MSr));
+    }
+  }
+}
+
+// ================================================================================================
+// adjoint kernels
+// ================================================================================================
+// transposed butterfly: on entry every lane holds 16 partial values v[0..15]; on exit lane j holds in
+// v[0] the sum over all 32 lanes of value (j & 15).
+__device__ __forceinline__ void warp_reduce16(double (&v)[16], int lane) {
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const double send = up ? v[i] : v[i + s];
+      const double keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+// cross-warp reduction of one chunk and store of the per-tile partial sums
+template <int NW>
+__device__ __forceinline__ void flush_chunk(const double (*s_red)[LEG_CHUNK * 4], double* gpart,
+                                            int tid_consumer, bool first) {
+  for (int i = tid_consumer; i < LEG_CHUNK * 4; i += NW * 32) {
+    double s = first ? 0.0 : gpart[i];  // same thread owns gpart[i] for the whole item
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += s_red[w][i];
+    gpart[i] = s;
+  }
+}
+
+// spin 0 adjoint: At_n = sum_pairs p_n (legN + legS), Bt_n = sum_pairs p_n x (legN - legS)
+// One work item = one m and a contiguous RANGE of pairs; the CTA walks the range tile by tile and
+// accumulates its own partial sums in global memory (read-modify-write by the same thread, L2
+// resident), so the number of partial buffers per m is the number of items, not of tiles.
+template <int R, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32) k_leg2alm_s0(LegParams P) {
+  __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
+  __shared__ double s_red[2][NW][LEG_CHUNK * 4];
+  __shared__ __align__(8) uint64_t s_full[NSTAGE];
+  __shared__ __align__(8) uint64_t s_empty[NSTAGE];
+  constexpr int TILE = R * NW * 32;
+
+  const WorkItem it = P.items[blockIdx.x];
+  const int mi = it.mi;
+  const int m = (int)P.mval[mi];
+  const int nn = (int)P.nstep[mi];
+  const int nsteps = (nn + LEG_GROUP - 1) / LEG_GROUP * LEG_GROUP;
+  const int nchunks = (nsteps + LEG_CHUNK - 1) / LEG_CHUNK;
+  const int ntile = (it.np + TILE - 1) / TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    if (lane == 0)
+      producer_loop<false>(nchunks, ntile, P.coef + (size_t)P.off[mi] * 2, nullptr, s_coef, nullptr,
+                           s_full, s_empty);
+    return;
+  }
+
+  const double2* leg = reinterpret_cast<const double2*>(P.leg);
+  const double k0 = P.k0[mi];
+  double* gpart = P.part + (size_t)P.partoff[blockIdx.x] * 4;
+  const int tidc = threadIdx.x;  // consumer threads are 0 .. NW*32-1
+  int cg = 0;                    // global chunk counter (pipeline position)
+
+  for (int tile = 0; tile < ntile; ++tile) {
+    const int tp0 = it.p0 + tile * TILE;
+    const int tnp = min(TILE, it.np - tile * TILE);
+    double csq[R], lam1[R], lam2[R];
+    double er[R], ei[R], orr[R], oi[R];
+    int sc[R];
+    bool act[R];
+    bool any_act = false;
+
+    auto load_in = [&](int r, int p) {
+      const int64_t rowoff = (int64_t)mi * P.mstr[p];
+      const double2 gN = leg[P.offN[p] + rowoff];
+      const int64_t oS = P.offS[p];
+      const double2 gS = oS >= 0 ? leg[oS + rowoff] : make_double2(0.0, 0.0);
+      const double cc = P.cth[p];
+      er[r] = gN.x + gS.x;
+      ei[r] = gN.y + gS.y;
+      orr[r] = cc * (gN.x - gS.x);
+      oi[r] = cc * (gN.y - gS.y);
+    };
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int pl = warp * 32 * R + r * 32 + lane;
+      const bool valid = pl < tnp;
+      const int p = tp0 + (valid ? pl : 0);
+      act[r] = valid && (m <= P.mlim[p]);
+      any_act |= act[r];
+      const double c = P.cth[p];
+      csq[r] = c * c;
+      double mant;
+      int e;
+      pow_scaled(P.sth[p], m, mant, e);
+      to_scaled(k0 * mant, e, lam2[r], sc[r]);
+      if (!act[r]) {
+        lam2[r] = 0.0;
+        sc[r] = 0;
+      }
+      lam1[r] = 0.0;
+      er[r] = ei[r] = orr[r] = oi[r] = 0.0;
+      if (act[r] && sc[r] == 0) load_in(r, p);
+    }
+    const bool warp_act = __any_sync(0xffffffffu, any_act);
+
+    for (int c = 0; c < nchunks; ++c, ++cg) {
+      const int st = cg % NSTAGE;
+      double* red = &s_red[cg & 1][warp][0];
+      mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
+      const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
+      for (int g = 0; g < LEG_CHUNK / LEG_GROUP; ++g) {
+        bool did = false;
+        if (warp_act && g < ng) {
+          bool mine0 = false, mineneg = false;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            mine0 |= act[r] && (sc[r] == 0);
+            mineneg |= (sc[r] < 0);
+          }
+          const bool any0 = __any_sync(0xffffffffu, mine0);
+          const Coef* cf = &s_coef[st][g * LEG_GROUP];
+          if (any0) {
+            did = true;
+#pragma unroll
+            for (int h = 0; h < LEG_GROUP / 4; ++h) {
+              double acc[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                const Coef ab = cf[h * 4 + s];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                  acc[4 * s + 0] = fma(lam2[r], er[r], acc[4 * s + 0]);
+                  acc[4 * s + 1] = fma(lam2[r], ei[r], acc[4 * s + 1]);
+                  acc[4 * s + 2] = fma(lam2[r], orr[r], acc[4 * s + 2]);
+                  acc[4 * s + 3] = fma(lam2[r], oi[r], acc[4 * s + 3]);
+                  const double t = fma(ab.a, csq[r], ab.b);
+                  const double nx = fma(t, lam2[r], lam1[r]);
+                  lam1[r] = lam2[r];
+                  lam2[r] = nx;
+                }
+              }
+              warp_reduce16(acc, lane);
+              if (lane < 16) red[(g * LEG_GROUP + h * 4) * 4 + lane] = acc[0];
+            }
+          } else {
+#pragma unroll
+            for (int s = 0; s < LEG_GROUP; ++s) {
+              const Coef ab = cf[s];
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const double t = fma(ab.a, csq[r], ab.b);
+                const double nx = fma(t, lam2[r], lam1[r]);
+                lam1[r] = lam2[r];
+                lam2[r] = nx;
+              }
+            }
+          }
+          if (__any_sync(0xffffffffu, mineneg)) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if (sc[r] < 0 && is_big(lam2[r])) {
+                lam1[r] *= SC_DOWN;
+                lam2[r] *= SC_DOWN;
+                sc[r] += 1;
+                // ring enters range: fetch its leg values now (masked to 0 until then)
+                if (sc[r] == 0) load_in(r, tp0 + warp * 32 * R + r * 32 + lane);
+              }
+            }
+          }
+        }
+        if (!did) red[g * LEG_GROUP * 4 + lane] = 0.0;  // 8 steps x 4 values = 32 doubles
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      named_bar_sync(1, NW * 32);
+      flush_chunk<NW>(s_red[cg & 1], gpart + (size_t)c * LEG_CHUNK * 4, tidc, tile == 0);
+    }
+  }
+}
+
+// spin 2 adjoint:  G+_l = sum_pairs [ d+ w+N + (-1)^(l+m) d- w+S ],  G-_l = sum_pairs [ d- w-N + (-1)^(l+m) d+ w-S ]
+//   w+- = legQ +- i legU
+template <int R, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32) k_leg2alm_s2(LegParams P) {
+  __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
+  __shared__ double s_red[2][NW][LEG_CHUNK * 4];
+  __shared__ __align__(8) uint64_t s_full[NSTAGE];
+  __shared__ __align__(8) uint64_t s_empty[NSTAGE];
+  constexpr int TILE = R * NW * 32;
+
+  const WorkItem it = P.items[blockIdx.x];
+  const int mi = it.mi;
+  const int m = (int)P.mval[mi];
+  const int nl = (int)P.nstep[mi];
+  const int nsteps = (nl + LEG_GROUP - 1) / LEG_GROUP * LEG_GROUP;
+  const int nchunks = (nsteps + LEG_CHUNK - 1) / LEG_CHUNK;
+  const int ntile = (it.np + TILE - 1) / TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    if (lane == 0)
+      producer_loop<false>(nchunks, ntile, P.coef + (size_t)P.off[mi] * 2, nullptr, s_coef, nullptr,
+                           s_full, s_empty);
+    return;
+  }
+
+  const double2* leg = reinterpret_cast<const double2*>(P.leg);
+  const double kp = P.k0[mi], km = P.k1[mi];
+  const int pw = m >= 2 ? m - 2 : 2 - m;
+  const int q = m < 2 ? m : 2;
+  const int l0 = m > 2 ? m : 2;
+  const double sgnS = ((l0 + m) & 1) ? -1.0 : 1.0;
+  double* gpart = P.part + (size_t)P.partoff[blockIdx.x] * 4;
+  const int tidc = threadIdx.x;
+  int cg = 0;
+
+  for (int tile = 0; tile < ntile; ++tile) {
+    const int tp0 = it.p0 + tile * TILE;
+    const int tnp = min(TILE, it.np - tile * TILE);
+    double x[R], lp1[R], lp2[R], lm1[R], lm2[R];
+    // masked inputs: wpN (x d+), wmS (x d+ x sign) live with scp ; wmN (x d-), wpS (x d- x sign) with scm
+    double wpNr[R], wpNi[R], wmSr[R], wmSi[R], wmNr[R], wmNi[R], wpSr[R], wpSi[R];
+    int scp[R], scm[R];
+    bool act[R];
+    bool any_act = false;
+
+    auto load_p = [&](int r, int p) {  // inputs multiplied by d+
+      const int64_t rowoff = (int64_t)mi * P.mstr[p];
+      const int64_t cs = P.cstr[p];
+      const double2 qN = leg[P.offN[p] + rowoff], uN = leg[P.offN[p] + rowoff + cs];
+      // w+N = Q + iU = (qr - ui, qi + ur)
+      wpNr[r] = qN.x - uN.y;
+      wpNi[r] = qN.y + uN.x;
+      const int64_t oS = P.offS[p];
+      if (oS >= 0) {
+        const double2 qS = leg[oS + rowoff], uS = leg[oS + rowoff + cs];
+        // w-S = Q - iU = (qr + ui, qi - ur)
+        wmSr[r] = sgnS * (qS.x + uS.y);
+        wmSi[r] = sgnS * (qS.y - uS.x);
+      } else {
+        wmSr[r] = wmSi[r] = 0.0;
+      }
+    };
+    auto load_m = [&](int r, int p) {  // inputs multiplied by d-
+      const int64_t rowoff = (int64_t)mi * P.mstr[p];
+      const int64_t cs = P.cstr[p];
+      const double2 qN = leg[P.offN[p] + rowoff], uN = leg[P.offN[p] + rowoff + cs];
+      wmNr[r] = qN.x + uN.y;
+      wmNi[r] = qN.y - uN.x;
+      const int64_t oS = P.offS[p];
+      if (oS >= 0) {
+        const double2 qS = leg[oS + rowoff], uS = leg[oS + rowoff + cs];
+        wpSr[r] = sgnS * (qS.x - uS.y);
+        wpSi[r] = sgnS * (qS.y + uS.x);
+      } else {
+        wpSr[r] = wpSi[r] = 0.0;
+      }
+    };
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int pl = warp * 32 * R + r * 32 + lane;
+      const bool valid = pl < tnp;
+      const int p = tp0 + (valid ? pl : 0);
+      act[r] = valid && (m <= P.mlim[p]);
+      any_act |= act[r];
+      x[r] = P.cth[p];
+      double mant;
+      int e;
+      pow_scaled(P.sth[p], pw, mant, e);
+      double fs = 1.0, fc = 1.0;
+      const double s2 = P.sh[p] * P.sh[p], c2 = P.ch[p] * P.ch[p];
+      for (int k = 0; k < q; ++k) {
+        fs *= s2;
+        fc *= c2;
+      }
+      to_scaled(kp * mant * fs, e, lp2[r], scp[r]);
+      to_scaled(km * mant * fc, e, lm2[r], scm[r]);
+      if (!act[r]) {
+        lp2[r] = lm2[r] = 0.0;
+        scp[r] = scm[r] = 0;
+      }
+      lp1[r] = lm1[r] = 0.0;
+      wpNr[r] = wpNi[r] = wmSr[r] = wmSi[r] = 0.0;
+      wmNr[r] = wmNi[r] = wpSr[r] = wpSi[r] = 0.0;
+      if (act[r] && scp[r] == 0) load_p(r, p);
+      if (act[r] && scm[r] == 0) load_m(r, p);
+    }
+    const bool warp_act = __any_sync(0xffffffffu, any_act);
+
+    for (int c = 0; c < nchunks; ++c, ++cg) {
+      const int st = cg % NSTAGE;
+      double* red = &s_red[cg & 1][warp][0];
+      mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
+      const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
+      for (int g = 0; g < LEG_CHUNK / LEG_GROUP; ++g) {
+        bool did = false;
+        if (warp_act && g < ng) {
+          bool mine0 = false, mineneg = false;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            mine0 |= act[r] && ((scp[r] == 0) || (scm[r] == 0));
+            mineneg |= (scp[r] < 0) || (scm[r] < 0);
+          }
+          const bool any0 = __any_sync(0xffffffffu, mine0);
+          const Coef* cf = &s_coef[st][g * LEG_GROUP];
+          if (any0) {
+            did = true;
+#pragma unroll
+            for (int h = 0; h < LEG_GROUP / 4; ++h) {
+              double acc[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                const Coef ab = cf[h * 4 + s];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                  // G+ : d+ w+N  +- d- w+S ; G- : d- w-N +- d+ w-S   (sign alternates with the step)
+                  acc[4 * s + 0] = fma(lp2[r], wpNr[r], acc[4 * s + 0]);
+                  acc[4 * s + 1] = fma(lp2[r], wpNi[r], acc[4 * s + 1]);
+                  acc[4 * s + 2] = fma(lm2[r], wmNr[r], acc[4 * s + 2]);
+                  acc[4 * s + 3] = fma(lm2[r], wmNi[r], acc[4 * s + 3]);
+                  if ((s & 1) == 0) {
+                    acc[4 * s + 0] = fma(lm2[r], wpSr[r], acc[4 * s + 0]);
+                    acc[4 * s + 1] = fma(lm2[r], wpSi[r], acc[4 * s + 1]);
+                    acc[4 * s + 2] = fma(lp2[r], wmSr[r], acc[4 * s + 2]);
+                    acc[4 * s + 3] = fma(lp2[r], wmSi[r], acc[4 * s + 3]);
+                  } else {
+                    acc[4 * s + 0] = fma(-lm2[r], wpSr[r], acc[4 * s + 0]);
+                    acc[4 * s + 1] = fma(-lm2[r], wpSi[r], acc[4 * s + 1]);
+                    acc[4 * s + 2] = fma(-lp2[r], wmSr[r], acc[4 * s + 2]);
+                    acc[4 * s + 3] = fma(-lp2[r], wmSi[r], acc[4 * s + 3]);
+                  }
+                  const double tp = fma(x[r], ab.a, ab.b);
+                  const double tm = fma(x[r], ab.a, -ab.b);
+                  const double np_ = fma(tp, lp2[r], -lp1[r]);
+                  const double nm_ = fma(tm, lm2[r], -lm1[r]);
+                  lp1[r] = lp2[r];
+                  lp2[r] = np_;
+                  lm1[r] = lm2[r];
+                  lm2[r] = nm_;
+                }
+              }
+              warp_reduce16(acc, lane);
+              if (lane < 16) red[(g * LEG_GROUP + h * 4) * 4 + lane] = acc[0];
+            }
+          } else {
+#pragma unroll
+            for (int s = 0; s < LEG_GROUP; ++s) {
+              const Coef ab = cf[s];
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const double tp = fma(x[r], ab.a, ab.b);
+                const double tm = fma(x[r], ab.a, -ab.b);
+                const double np_ = fma(tp, lp2[r], -lp1[r]);
+                const double nm_ = fma(tm, lm2[r], -lm1[r]);
+                lp1[r] = lp2[r];
+                lp2[r] = np_;
+                lm1[r] = lm2[r];
+                lm2[r] = nm_;
+              }
+            }
+          }
+          if (__any_sync(0xffffffffu, mineneg)) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const int p = tp0 + warp * 32 * R + r * 32 + lane;
+              if (scp[r] < 0 && is_big(lp2[r])) {
+                lp1[r] *= SC_DOWN;
+                lp2[r] *= SC_DOWN;
+                scp[r] += 1;
+                if (scp[r] == 0) load_p(r, p);
+              }
+              if (scm[r] < 0 && is_big(lm2[r])) {
+                lm1[r] *= SC_DOWN;
+                lm2[r] *= SC_DOWN;
+                scm[r] += 1;
+                if (scm[r] == 0) load_m(r, p);
+              }
+            }
+          }
+        }
+        if (!did) red[g * LEG_GROUP * 4 + lane] = 0.0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      named_bar_sync(1, NW * 32);
+      flush_chunk<NW>(s_red[cg & 1], gpart + (size_t)c * LEG_CHUNK * 4, tidc, tile == 0);
+    }
+  }
+}
+
+// ================================================================================================
+// prep / post kernels (HBM-bound, O(nalm))
+// ================================================================================================
+// spin 0 prep: stream[off+n] = { (eps_{l+1} a_l + eps_{l+2} a_{l+2}) / s_n , a_{l+1} / s_n }, l = m+2n
+__device__ __forceinline__ double eps_lm(int64_t l, int64_t m) {
+  return sqrt((double)(l * l - m * m) / (double)(4 * l * l - 1));
+}
+
+__global__ void k_prep_s0(const double2* __restrict__ alm, const int64_t* __restrict__ mval,
+                          const int64_t* __restrict__ mstart, const int64_t* __restrict__ nstep,
+                          const int64_t* __restrict__ off, const double* __restrict__ invs,
+                          int64_t lmax, Strm* __restrict__ stream) {
+  const int mi = blockIdx.y;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nstep[mi]) return;
+  const int64_t m = mval[mi];
+  const int64_t l = m + 2 * n;
+  const double2* a = alm + mstart[mi];
+  const double2 al = a[l];
+  const double2 al1 = (l + 1 <= lmax) ? a[l + 1] : make_double2(0.0, 0.0);
+  const double2 al2 = (l + 2 <= lmax) ? a[l + 2] : make_double2(0.0, 0.0);
+  const double e1 = eps_lm(l + 1, m), e2 = eps_lm(l + 2, m);
+  const double is = invs[off[mi] + n];
+  Strm o;
+  o.x = fma(e1, al.x, e2 * al2.x) * is;
+  o.y = fma(e1, al.y, e2 * al2.y) * is;
+  o.z = al1.x * is;
+  o.w = al1.y * is;
+  stream[off[mi] + n] = o;
+}
+
+// spin 2 prep: alpha+ = -(E + iB) sigma/2 ; alpha- = -(E - iB) sigma/2
+__global__ void k_prep_s2(const double2* __restrict__ almE, const double2* __restrict__ almB,
+                          const int64_t* __restrict__ mval, const int64_t* __restrict__ mstart,
+                          const int64_t* __restrict__ nstep, const int64_t* __restrict__ off,
+                          const double* __restrict__ sig, Strm* __restrict__ stream) {
+  const int mi = blockIdx.y;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nstep[mi]) return;
+  const int64_t m = mval[mi];
+  const int64_t l = (m > 2 ? m : 2) + j;
+  const double2 e = almE[mstart[mi] + l];
+  const double2 b = almB[mstart[mi] + l];
+  const double h = -0.5 * sig[off[mi] + j];
+  Strm o;
+  // E + iB = (er - bi, ei + br) ; E - iB = (er + bi, ei - br)
+  o.x = h * (e.x - b.y);
+  o.y = h * (e.y + b.x);
+  o.z = h * (e.x + b.y);
+  o.w = h * (e.y - b.x);
+  stream[off[mi] + j] = o;
+}
+
+// adjoint: sum the per-tile partials of one m (deterministic order)
+__global__ void k_reduce_part(const Strm* __restrict__ part, const int64_t* __restrict__ partoff,
+                              const int* __restrict__ afirst, const int* __restrict__ acount,
+                              const int64_t* __restrict__ nstep, const int64_t* __restrict__ off,
+                              Strm* __restrict__ accum) {
+  const int mi = blockIdx.y;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nstep[mi]) return;
+  Strm s = {0.0, 0.0, 0.0, 0.0};
+  const int f = afirst[mi], cnt = acount[mi];
+  for (int i = 0; i < cnt; ++i) {
+    const Strm v = part[partoff[f + i] + n];
+    s.x += v.x;
+    s.y += v.y;
+    s.z += v.z;
+    s.w += v.w;
+  }
+  accum[off[mi] + n] = s;
+}
+
+// spin 0 post: a_l = eps_{l+1} At_n/s_n + eps_l At_{n-1}/s_{n-1} (l = m+2n) ; a_{l+1} = Bt_n/s_n
+__global__ void k_post_s0(const Strm* __restrict__ accum, const int64_t* __restrict__ mval,
+                          const int64_t* __restrict__ mstart, const int64_t* __restrict__ nstep,
+                          const int64_t* __restrict__ off, const double* __restrict__ invs,
+                          int64_t lmax, double2* __restrict__ alm) {
+  const int mi = blockIdx.y;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nstep[mi]) return;
+  const int64_t m = mval[mi];
+  const int64_t l = m + 2 * n;
+  const Strm cur = accum[off[mi] + n];
+  const double is = invs[off[mi] + n];
+  const double e1 = eps_lm(l + 1, m);
+  double vr = e1 * is * cur.x, vi = e1 * is * cur.y;
+  if (n > 0) {
+    const Strm prv = accum[off[mi] + n - 1];
+    const double isp = invs[off[mi] + n - 1];
+    const double e0 = eps_lm(l, m);
+    vr = fma(e0 * isp, prv.x, vr);
+    vi = fma(e0 * isp, prv.y, vi);
+  }
+  double2* a = alm + mstart[mi];
+  a[l] = make_double2(vr, vi);
+  if (l + 1 <= lmax) a[l + 1] = make_double2(is * cur.z, is * cur.w);
+}
+
+// spin 2 post: E = -sigma/2 (G+ + G-) ; B = i sigma/2 (G+ - G-) ; l < 2 entries zeroed
+__global__ void k_post_s2(const Strm* __restrict__ accum, const int64_t* __restrict__ mval,
+                          const int64_t* __restrict__ mstart, const int64_t* __restrict__ nstep,
+                          const int64_t* __restrict__ off, const double* __restrict__ sig,
+                          int64_t lmax, double2* __restrict__ almE, double2* __restrict__ almB) {
+  const int mi = blockIdx.y;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m = mval[mi];
+  if (j == 0 && blockIdx.x == 0) {
+    for (int64_t l = m; l < 2 && l <= lmax; ++l) {
+      almE[mstart[mi] + l] = make_double2(0.0, 0.0);
+      almB[mstart[mi] + l] = make_double2(0.0, 0.0);
+    }
+  }
+  if (j >= nstep[mi]) return;
+  const int64_t l = (m > 2 ? m : 2) + j;
+  const Strm g = accum[off[mi] + j];
+  const double h = 0.5 * sig[off[mi] + j];
+  almE[mstart[mi] + l] = make_double2(-h * (g.x + g.z), -h * (g.y + g.w));
+  // i * (dr, di) = (-di, dr)
+  almB[mstart[mi] + l] = make_double2(-h * (g.y - g.w), h * (g.x - g.z));
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+std::vector<PairHost> build_pairs(int64_t lmax, int64_t nring, const double* theta) {
+  std::vector<int64_t> idx((size_t)nring);
+  for (int64_t i = 0; i < nring; ++i) idx[(size_t)i] = i;
+  std::stable_sort(idx.begin(), idx.end(),
+                   [&](int64_t a, int64_t b) { return theta[a] < theta[b]; });
+  const double pi = 3.14159265358979323846;
+  auto mk = [&](int64_t n, int64_t s) {
+    PairHost p;
+    const long double th = (long double)theta[n];
+    p.cth = (double)cosl(th);
+    p.sth = (double)sinl(th);
+    p.sh = (double)sinl(0.5L * th);
+    p.ch = (double)cosl(0.5L * th);
+    p.slotN = n;
+    p.slotS = s;
+    p.mlim0 = (int)mlim_rule(lmax, 0, p.sth, p.cth);
+    p.mlim2 = (int)mlim_rule(lmax, 2, p.sth, p.cth);
+    return p;
+  };
+  std::vector<PairHost> out;
+  out.reserve((size_t)nring / 2 + 1);
+  int64_t lo = 0, hi = nring - 1;
+  while (lo <= hi) {
+    const int64_t a = idx[(size_t)lo], b = idx[(size_t)hi];
+    if (lo < hi && std::fabs(theta[a] + theta[b] - pi) <= 1e-14 * pi && theta[a] < 0.5 * pi) {
+      out.push_back(mk(a, b));
+      ++lo;
+      --hi;
+    } else if (std::fabs(theta[a] - 0.5 * pi) >= std::fabs(theta[b] - 0.5 * pi)) {
+      out.push_back(mk(a, -1));
+      ++lo;
+    } else {
+      out.push_back(mk(b, -1));
+      --hi;
+    }
+  }
+  return out;
+}
+
+LegendreStage::~LegendreStage() {
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+}
+
+double LegendreStage::main_kernel_ms() const {
+  float f = 0.f;
+  if (ev0_ && ev1_ && cudaEventElapsedTime(&f, ev0_, ev1_) != cudaSuccess) {
+    cudaGetLastError();
+    f = 0.f;
+  }
+  return (double)f;
+}
+
+namespace {
+// kernel configurations
+constexpr int S0_R = 4, S0_NW = 4;   // spin-0 synthesis: 512 pairs / tile
+constexpr int S2_R = 2, S2_NW = 4;   // spin-2 synthesis: 256 pairs / tile
+constexpr int A0_R = 4, A0_NW = 4;   // spin-0 adjoint:   512 pairs / tile
+constexpr int A2_R = 2, A2_NW = 4;   // spin-2 adjoint:   256 pairs / tile
+
+// Work list: for every local m (ascending == descending cost; CTAs are handed out in blockIdx
+// order) the active tiles, i.e. those holding at least one pair with mlim >= m.  Pairs are sorted
+// pole -> equator and mlim grows towards the equator, so the active pairs of an m form a suffix.
+//   groups == 0 : one item per active tile (synthesis)
+//   groups  > 0 : the active tile range of each m is split into <= groups contiguous multi-tile
+//                 items (adjoint; each item owns one partial-sum buffer)
+void make_items(const std::vector<PairHost>& pairs, const std::vector<int64_t>& mval,
+                const std::vector<int64_t>& nstep, bool spin2, int tile, int groups,
+                std::vector<WorkItem>& items, std::vector<int>* first, std::vector<int>* count) {
+  const int np = (int)pairs.size();
+  const int ntile = (np + tile - 1) / tile;
+  std::vector<int> tmax((size_t)ntile, -1);
+  for (int t = 0; t < ntile; ++t)
+    for (int p = t * tile; p < std::min(np, (t + 1) * tile); ++p)
+      tmax[(size_t)t] = std::max(tmax[(size_t)t], spin2 ? pairs[(size_t)p].mlim2 : pairs[(size_t)p].mlim0);
+  items.clear();
+  if (first) first->assign(mval.size(), 0);
+  if (count) count->assign(mval.size(), 0);
+  for (size_t mi = 0; mi < mval.size(); ++mi) {
+    if (first) (*first)[mi] = (int)items.size();
+    if (nstep[mi] <= 0) continue;
+    std::vector<int> active;
+    for (int t = ntile - 1; t >= 0; --t)
+      if (tmax[(size_t)t] >= mval[mi]) active.push_back(t);
+    if (groups == 0) {
+      for (int t : active) {
+        WorkItem w;
+        w.mi = (int)mi;
+        w.p0 = t * tile;
+        w.np = std::min(np, (t + 1) * tile) - t * tile;
+        w.part = 0;
+        items.push_back(w);
+      }
+    } else if (!active.empty()) {
+      // active tiles are not necessarily contiguous for exotic theta lists; cover [tmin, tmax]
+      const int tlo = *std::min_element(active.begin(), active.end());
+      const int thi = *std::max_element(active.begin(), active.end());
+      const int nt = thi - tlo + 1;
+      const int G = std::min(groups, nt);
+      for (int g = 0; g < G; ++g) {
+        const int ta = tlo + (int)((int64_t)nt * g / G), tb = tlo + (int)((int64_t)nt * (g + 1) / G);
+        WorkItem w;
+        w.mi = (int)mi;
+        w.p0 = ta * tile;
+        w.np = std::min(np, tb * tile) - ta * tile;
+        w.part = 0;
+        items.push_back(w);
+      }
+    }
+    if (count) (*count)[mi] = (int)items.size() - (*first)[mi];
+  }
+}
+}  // namespace
+
+void LegendreStage::setup(int64_t lmax, const int64_t* mval, const int64_t* mstart, int64_t nm,
+                          int64_t nring, const double* theta, const LegLayout& layout, int max_ncomp,
+                          cudaStream_t stream) {
+  lmax_ = lmax;
+  nm_ = nm;
+  nring_ = nring;
+  max_ncomp_ = max_ncomp;
+  mval_.assign(mval, mval + nm);
+  mstart_.assign(mstart, mstart + nm);
+  layout_ = layout;
+  HP_REQUIRE((int64_t)layout.base.size() == nring, HPSHT_ERR_INTERNAL, "layout size mismatch");
+  pairs_ = build_pairs(lmax, nring, theta);
+  npairs_ = (int64_t)pairs_.size();
+  HP_REQUIRE(npairs_ < (1ll << 30) && nm < (1ll << 30), HPSHT_ERR_UNSUPPORTED, "problem too large");
+
+  std::vector<double> cth((size_t)npairs_), sth((size_t)npairs_), sh((size_t)npairs_), ch((size_t)npairs_);
+  std::vector<int> ml0((size_t)npairs_), ml2((size_t)npairs_);
+  std::vector<int64_t> offN((size_t)npairs_), offS((size_t)npairs_), mstr((size_t)npairs_), cstr((size_t)npairs_);
+  culled0_ = culled2_ = dense_ = 0;
+  for (int64_t p = 0; p < npairs_; ++p) {
+    const PairHost& q = pairs_[(size_t)p];
+    cth[(size_t)p] = q.cth;
+    sth[(size_t)p] = q.sth;
+    sh[(size_t)p] = q.sh;
+    ch[(size_t)p] = q.ch;
+    ml0[(size_t)p] = q.mlim0;
+    ml2[(size_t)p] = q.mlim2;
+    offN[(size_t)p] = layout.base[(size_t)q.slotN];
+    mstr[(size_t)p] = layout.mstride[(size_t)q.slotN];
+    cstr[(size_t)p] = layout.cstride[(size_t)q.slotN];
+    if (q.slotS >= 0) {
+      offS[(size_t)p] = layout.base[(size_t)q.slotS];
+      HP_REQUIRE(layout.mstride[(size_t)q.slotS] == mstr[(size_t)p] &&
+                     layout.cstride[(size_t)q.slotS] == cstr[(size_t)p],
+                 HPSHT_ERR_INTERNAL, "N/S rings of a pair must share strides");
+    } else {
+      offS[(size_t)p] = -1;
+    }
+    for (int64_t i = 0; i < nm; ++i) {
+      const double w = (double)(lmax - mval[i] + 1);
+      if (w <= 0) continue;
+      dense_ += w;
+      if (mval[i] <= q.mlim0) culled0_ += w;
+      if (mval[i] <= q.mlim2) culled2_ += w;
+    }
+  }
+  d_cth_.upload(cth.data(), cth.size(), stream);
+  d_sth_.upload(sth.data(), sth.size(), stream);
+  d_sh_.upload(sh.data(), sh.size(), stream);
+  d_ch_.upload(ch.data(), ch.size(), stream);
+  d_mlim0_.upload(ml0.data(), ml0.size(), stream);
+  d_mlim2_.upload(ml2.data(), ml2.size(), stream);
+  d_offN_.upload(offN.data(), offN.size(), stream);
+  d_offS_.upload(offS.data(), offS.size(), stream);
+  d_mstr_.upload(mstr.data(), mstr.size(), stream);
+  d_cstr_.upload(cstr.data(), cstr.size(), stream);
+  d_mval_.upload(mval_.data(), mval_.size(), stream);
+  d_mstart_.upload(mstart_.data(), mstart_.size(), stream);
+  HP_CUDA(cudaStreamSynchronize(stream));
+  if (!ev0_) HP_CUDA(cudaEventCreate(&ev0_));
+  if (!ev1_) HP_CUDA(cudaEventCreate(&ev1_));
+  have0_ = have2_ = false;
+}
+
+void LegendreStage::ensure_spin(int spin, cudaStream_t stream) {
+  if ((spin == 0 && have0_) || (spin != 0 && have2_)) return;
+  LegendreTables T;
+  build_legendre_tables(lmax_, mval_.data(), nm_, LEG_CHUNK, spin == 0, spin != 0, T);
+  size_t part_steps = 0;
+  // enough adjoint items to fill the GPU several times over even when a rank owns few m's
+  const int adj_groups = (int)std::max<int64_t>(1, (4096 + nm_ - 1) / std::max<int64_t>(nm_, 1));
+  if (spin == 0) {
+    d_nstep0_.upload(T.nstep0.data(), T.nstep0.size(), stream);
+    d_off0_.upload(T.off0.data(), T.off0.size(), stream);
+    d_coef0_.upload(T.coef0.data(), T.coef0.size(), stream);
+    d_invs0_.upload(T.invs0.data(), T.invs0.size(), stream);
+    d_k0_.upload(T.k0.data(), T.k0.size(), stream);
+    d_stream0_.alloc((size_t)T.off0[(size_t)nm_] * 4);
+    d_stream0_.zero(stream);
+    make_items(pairs_, mval_, T.nstep0, false, S0_R * S0_NW * 32, 0, items_s0_, nullptr, nullptr);
+    make_items(pairs_, mval_, T.nstep0, false, A0_R * A0_NW * 32, adj_groups, items_a0_, &afirst0_, &acount0_);
+    apartoff0_.resize(items_a0_.size());
+    for (size_t i = 0; i < items_a0_.size(); ++i) {
+      apartoff0_[i] = (int64_t)part_steps;
+      part_steps += (size_t)round_up(T.nstep0[(size_t)items_a0_[i].mi], LEG_CHUNK);
+    }
+    d_items_s0_.upload(items_s0_.data(), items_s0_.size(), stream);
+    d_items_a0_.upload(items_a0_.data(), items_a0_.size(), stream);
+    d_afirst0_.upload(afirst0_.data(), afirst0_.size(), stream);
+    d_acount0_.upload(acount0_.data(), acount0_.size(), stream);
+    d_apartoff0_.upload(apartoff0_.data(), apartoff0_.size(), stream);
+    nstep0_h_ = T.nstep0;
+    off0_h_ = T.off0;
+    have0_ = true;
+  } else {
+    d_nstep2_.upload(T.nstep2.data(), T.nstep2.size(), stream);
+    d_off2_.upload(T.off2.data(), T.off2.size(), stream);
+    d_coef2_.upload(T.coef2.data(), T.coef2.size(), stream);
+    d_sig2_.upload(T.sig2.data(), T.sig2.size(), stream);
+    d_kp2_.upload(T.kp2.data(), T.kp2.size(), stream);
+    d_km2_.upload(T.km2.data(), T.km2.size(), stream);
+    d_stream2_.alloc((size_t)T.off2[(size_t)nm_] * 4);
+    d_stream2_.zero(stream);
+    make_items(pairs_, mval_, T.nstep2, true, S2_R * S2_NW * 32, 0, items_s2_, nullptr, nullptr);
+    make_items(pairs_, mval_, T.nstep2, true, A2_R * A2_NW * 32, adj_groups, items_a2_, &afirst2_, &acount2_);
+    apartoff2_.resize(items_a2_.size());
+    for (size_t i = 0; i < items_a2_.size(); ++i) {
+      apartoff2_[i] = (int64_t)part_steps;
+      part_steps += (size_t)round_up(T.nstep2[(size_t)items_a2_[i].mi], LEG_CHUNK);
+    }
+    d_items_s2_.upload(items_s2_.data(), items_s2_.size(), stream);
+    d_items_a2_.upload(items_a2_.data(), items_a2_.size(), stream);
+    d_afirst2_.upload(afirst2_.data(), afirst2_.size(), stream);
+    d_acount2_.upload(acount2_.data(), acount2_.size(), stream);
+    d_apartoff2_.upload(apartoff2_.data(), apartoff2_.size(), stream);
+    nstep2_h_ = T.nstep2;
+    off2_h_ = T.off2;
+    have2_ = true;
+  }
+  part_steps_need_ = std::max(part_steps_need_, part_steps);
+  accum_steps_need_ = std::max(accum_steps_need_,
+                               (size_t)(spin == 0 ? T.off0[(size_t)nm_] : T.off2[(size_t)nm_]));
+  HP_CUDA(cudaStreamSynchronize(stream));  // host vectors of T die here
+}
+
+static inline int64_t max_of(const std::vector<int64_t>& v) {
+  int64_t m = 0;
+  for (int64_t x : v) m = std::max(m, x);
+  return m;
+}
+
+void LegendreStage::alm2leg(const double* d_alm, int64_t alm_cstride, double* d_leg,
+                            int64_t leg_elems, int ncomp, cudaStream_t stream) {
+  const int spin = ncomp == 1 ? 0 : 2;
+  ensure_spin(spin, stream);
+  // (m, ring) combinations beyond mlim are never visited by a CTA: their leg is exactly 0
+  HP_CUDA(cudaMemsetAsync(d_leg, 0, (size_t)leg_elems * 2 * sizeof(double), stream));
+  LegParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.mval = d_mval_.p;
+  P.cth = d_cth_.p;
+  P.sth = d_sth_.p;
+  P.sh = d_sh_.p;
+  P.ch = d_ch_.p;
+  P.offN = d_offN_.p;
+  P.offS = d_offS_.p;
+  P.mstr = d_mstr_.p;
+  P.cstr = d_cstr_.p;
+  P.leg = d_leg;
+  const int TB = 256;
+  if (spin == 0) {
+    const int64_t mx = max_of(nstep0_h_);
+    if (mx > 0) {
+      dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
+      k_prep_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(d_alm), d_mval_.p,
+                                         d_mstart_.p, d_nstep0_.p, d_off0_.p, d_invs0_.p, lmax_,
+                                         reinterpret_cast<Strm*>(d_stream0_.p));
+      ++launches_;
+    }
+    P.items = d_items_s0_.p;
+    P.nstep = d_nstep0_.p;
+    P.off = d_off0_.p;
+    P.coef = d_coef0_.p;
+    P.k0 = d_k0_.p;
+    P.mlim = d_mlim0_.p;
+    P.stream = d_stream0_.p;
+    if (!items_s0_.empty()) {
+      cudaEventRecord(ev0_, stream);
+      k_alm2leg_s0<S0_R, S0_NW><<<(unsigned)items_s0_.size(), (S0_NW + 1) * 32, 0, stream>>>(P);
+      cudaEventRecord(ev1_, stream);
+      ++launches_;
+    }
+  } else {
+    const int64_t mx = max_of(nstep2_h_);
+    if (mx > 0) {
+      dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
+      k_prep_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(d_alm),
+                                         reinterpret_cast<const double2*>(d_alm) + alm_cstride,
+                                         d_mval_.p, d_mstart_.p, d_nstep2_.p, d_off2_.p, d_sig2_.p,
+                                         reinterpret_cast<Strm*>(d_stream2_.p));
+      ++launches_;
+    }
+    P.items = d_items_s2_.p;
+    P.nstep = d_nstep2_.p;
+    P.off = d_off2_.p;
+    P.coef = d_coef2_.p;
+    P.k0 = d_kp2_.p;
+    P.k1 = d_km2_.p;
+    P.mlim = d_mlim2_.p;
+    P.stream = d_stream2_.p;
+    if (!items_s2_.empty()) {
+      cudaEventRecord(ev0_, stream);
+      k_alm2leg_s2<S2_R, S2_NW><<<(unsigned)items_s2_.size(), (S2_NW + 1) * 32, 0, stream>>>(P);
+      cudaEventRecord(ev1_, stream);
+      ++launches_;
+    }
+  }
+  HP_CUDA(cudaGetLastError());
+}
+
+void LegendreStage::leg2alm(const double* d_leg, double* d_alm, int64_t alm_cstride, int ncomp,
+                            cudaStream_t stream) {
+  const int spin = ncomp == 1 ? 0 : 2;
+  ensure_spin(spin, stream);
+  d_part_.ensure(part_steps_need_ * 4);
+  d_accum_.ensure(accum_steps_need_ * 4);
+  LegParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.mval = d_mval_.p;
+  P.cth = d_cth_.p;
+  P.sth = d_sth_.p;
+  P.sh = d_sh_.p;
+  P.ch = d_ch_.p;
+  P.offN = d_offN_.p;
+  P.offS = d_offS_.p;
+  P.mstr = d_mstr_.p;
+  P.cstr = d_cstr_.p;
+  P.leg = const_cast<double*>(d_leg);
+  P.part = d_part_.p;
+  const int TB = 256;
+  if (spin == 0) {
+    P.items = d_items_a0_.p;
+    P.nstep = d_nstep0_.p;
+    P.off = d_off0_.p;
+    P.coef = d_coef0_.p;
+    P.k0 = d_k0_.p;
+    P.mlim = d_mlim0_.p;
+    P.partoff = d_apartoff0_.p;
+    if (!items_a0_.empty()) {
+      cudaEventRecord(ev0_, stream);
+      k_leg2alm_s0<A0_R, A0_NW><<<(unsigned)items_a0_.size(), (A0_NW + 1) * 32, 0, stream>>>(P);
+      cudaEventRecord(ev1_, stream);
+      ++launches_;
+    }
+    const int64_t mx = max_of(nstep0_h_);
+    if (mx > 0) {
+      dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
+      k_reduce_part<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p),
+                                             d_apartoff0_.p, d_afirst0_.p, d_acount0_.p,
+                                             d_nstep0_.p, d_off0_.p,
+                                             reinterpret_cast<Strm*>(d_accum_.p));
+      k_post_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_accum_.p), d_mval_.p,
+                                         d_mstart_.p, d_nstep0_.p, d_off0_.p, d_invs0_.p, lmax_,
+                                         reinterpret_cast<double2*>(d_alm));
+      launches_ += 2;
+    }
+  } else {
+    P.items = d_items_a2_.p;
+    P.nstep = d_nstep2_.p;
+    P.off = d_off2_.p;
+    P.coef = d_coef2_.p;
+    P.k0 = d_kp2_.p;
+    P.k1 = d_km2_.p;
+    P.mlim = d_mlim2_.p;
+    P.partoff = d_apartoff2_.p;
+    if (!items_a2_.empty()) {
+      cudaEventRecord(ev0_, stream);
+      k_leg2alm_s2<A2_R, A2_NW><<<(unsigned)items_a2_.size(), (A2_NW + 1) * 32, 0, stream>>>(P);
+      cudaEventRecord(ev1_, stream);
+      ++launches_;
+    }
+    int64_t mx = max_of(nstep2_h_);
+    mx = std::max<int64_t>(mx, 1);  // the post kernel also zeroes l < 2
+    dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
+    k_reduce_part<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p), d_apartoff2_.p,
+                                           d_afirst2_.p, d_acount2_.p, d_nstep2_.p, d_off2_.p,
+                                           reinterpret_cast<Strm*>(d_accum_.p));
+    k_post_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_accum_.p), d_mval_.p,
+                                       d_mstart_.p, d_nstep2_.p, d_off2_.p, d_sig2_.p, lmax_,
+                                       reinterpret_cast<double2*>(d_alm),
+                                       reinterpret_cast<double2*>(d_alm) + alm_cstride);
+    launches_ += 2;
+  }
+  HP_CUDA(cudaGetLastError());
+}
+
+}  // namespace hpsht

@@ -1,0 +1,644 @@
+// ringfft.cu — batched variable-length real FFTs of the ring stage (leg2map / map2leg), sm_100a.
+//
+// Replaces Ducc0.Sht.leg2map! (reference src/sht.jl:93) and Ducc0.Sht.map2leg! (src/sht.jl:169).
+//
+// One CTA transforms one ring of one component entirely in shared memory:
+//   leg2map:  load leg row (coalesced) -> phase shift exp(i m phi0) + alias fold onto the half-complex
+//             spectrum X[0..n/2] -> real inverse FFT of length n = 4r -> coalesced double2 pixel stores.
+//   map2leg:  the exact transpose.
+// The length-n real transform is reduced to two complex transforms of length r = n/4:
+//   Zc[k] = (X[k] + conj X[N-k]) + i w^k (X[k] - conj X[N-k]),  N = 2r, w = exp(2 pi i / n)
+//   u[k] = Zc[k] + Zc[k+r],  v[k] = (Zc[k] - Zc[k+r]) w^{2k},   U = IDFT_r(u), V = IDFT_r(v)
+//   x[4j..4j+3] = Re U[j], Im U[j], Re V[j], Im V[j]
+// IDFT_r is a radix-4 in-place power-of-two FFT when r is a power of two (the whole equatorial belt)
+// and a Bluestein chirp-z convolution of power-of-two length M >= 2r-1 otherwise (polar caps, where
+// r runs over every integer and is frequently prime).  The forward DIF leaves its output in
+// bit-reversed order, the chirp spectrum is stored in that order and the inverse DIT consumes it, so
+// no reordering pass is needed inside the convolution.
+// Rings are grouped by size class (threads / shared memory per CTA) at plan time.
+#include "ringfft.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace hpsht {
+
+namespace {
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
+  return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+// multiply by +i (INV) or -i (forward)
+template <bool INV>
+__device__ __forceinline__ double2 mul_pm_i(double2 a) {
+  return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+template <bool INV>
+__device__ __forceinline__ double2 twiddle(const double2* __restrict__ tw, int idx) {
+  const double2 t = __ldg(&tw[idx]);
+  return INV ? make_double2(t.x, -t.y) : t;
+}
+
+// exp(i m phi0) with the rounding error of the product m*phi0 compensated
+__device__ __forceinline__ double2 phase(int m, double phi0) {
+  const double dm = (double)m;
+  const double p = dm * phi0;
+  const double e = fma(dm, phi0, -p);
+  double s, c;
+  sincos(p, &s, &c);
+  return make_double2(fma(-e, s, c), fma(e, c, s));
+}
+
+// n-th roots of unity through a two-level table: W(q) = exp(2 pi i q / n) = hi[q>>6] * lo[q&63]
+struct Roots {
+  const double2* hi;
+  const double2* lo;
+  __device__ __forceinline__ double2 operator()(int q) const { return cmul(hi[q >> 6], lo[q & 63]); }
+};
+__device__ __forceinline__ void build_roots(double2* hi, double2* lo, int n, int tid, int nt) {
+  const int nhi = (n >> 6) + 1;
+  const double inv = 1.0 / (double)n;
+  for (int i = tid; i < nhi + 64; i += nt) {
+    const bool is_lo = i >= nhi;
+    const int q = is_lo ? (i - nhi) : (i << 6);
+    double s, c;
+    sincospi(2.0 * (double)q * inv, &s, &c);
+    if (is_lo)
+      lo[i - nhi] = make_double2(c, s);
+    else
+      hi[i] = make_double2(c, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// in-place power-of-two FFT passes over shared memory (all threads of the CTA participate)
+//   DIF: natural order in, bit-reversed out.  DIT: bit-reversed in, natural out.
+//   INV = false: exp(-2 pi i jk/M);  INV = true: exp(+2 pi i jk/M).  Unnormalised.
+//   tw[k] = exp(-2 pi i k / twn), k < twn/2, twn >= M.
+// ------------------------------------------------------------------------------------------------
+template <bool INV>
+__device__ void fft_dif(double2* buf, int M, const double2* __restrict__ tw, int twn, int tid, int nt) {
+  if (M < 2) return;
+  const int lg = 31 - __clz(M);
+  int L = M;
+  if (lg & 1) {
+    const int h = L >> 1;
+    const int ts = twn / L;
+    for (int i = tid; i < h; i += nt) {
+      const double2 a = buf[i], b = buf[i + h];
+      buf[i] = cadd(a, b);
+      buf[i + h] = cmul(csub(a, b), twiddle<INV>(tw, i * ts));
+    }
+    L >>= 1;
+    __syncthreads();
+  }
+  while (L >= 4) {
+    const int q = L >> 2;
+    const int lq = 31 - __clz(q);
+    const int ts = twn / L;
+    for (int i = tid; i < (M >> 2); i += nt) {
+      const int j = i & (q - 1);
+      const int b = ((i >> lq) * L) + j;
+      const double2 x0 = buf[b], x1 = buf[b + q], x2 = buf[b + 2 * q], x3 = buf[b + 3 * q];
+      const double2 w1 = twiddle<INV>(tw, j * ts);
+      const double2 w2 = twiddle<INV>(tw, 2 * j * ts);
+      const double2 a0 = cadd(x0, x2), a2 = cmul(csub(x0, x2), w1);
+      const double2 a1 = cadd(x1, x3), a3 = mul_pm_i<INV>(cmul(csub(x1, x3), w1));
+      buf[b] = cadd(a0, a1);
+      buf[b + q] = cmul(csub(a0, a1), w2);
+      buf[b + 2 * q] = cadd(a2, a3);
+      buf[b + 3 * q] = cmul(csub(a2, a3), w2);
+    }
+    L >>= 2;
+    __syncthreads();
+  }
+}
+
+template <bool INV>
+__device__ void fft_dit(double2* buf, int M, const double2* __restrict__ tw, int twn, int tid, int nt) {
+  if (M < 2) return;
+  const int lg = 31 - __clz(M);
+  int L = 1;
+  if (lg & 1) {
+    for (int i = tid; i < (M >> 1); i += nt) {
+      const double2 a = buf[2 * i], b = buf[2 * i + 1];
+      buf[2 * i] = cadd(a, b);
+      buf[2 * i + 1] = csub(a, b);
+    }
+    L = 2;
+    __syncthreads();
+  }
+  while (L < M) {
+    L <<= 2;
+    const int q = L >> 2;
+    const int lq = 31 - __clz(q);
+    const int ts = twn / L;
+    for (int i = tid; i < (M >> 2); i += nt) {
+      const int j = i & (q - 1);
+      const int b = ((i >> lq) * L) + j;
+      const double2 x0 = buf[b], x1 = buf[b + q], x2 = buf[b + 2 * q], x3 = buf[b + 3 * q];
+      const double2 w1 = twiddle<INV>(tw, j * ts);
+      const double2 w2 = twiddle<INV>(tw, 2 * j * ts);
+      const double2 t1 = cmul(x1, w2), t3 = cmul(x3, w2);
+      const double2 a0 = cadd(x0, t1), a1 = csub(x0, t1);
+      const double2 a2 = cadd(x2, t3), a3 = csub(x2, t3);
+      const double2 s2 = cmul(a2, w1), s3 = mul_pm_i<INV>(cmul(a3, w1));
+      buf[b] = cadd(a0, s2);
+      buf[b + 2 * q] = csub(a0, s2);
+      buf[b + q] = cadd(a1, s3);
+      buf[b + 3 * q] = csub(a1, s3);
+    }
+    __syncthreads();
+  }
+}
+
+__device__ void bitrev_permute(double2* buf, int M, int tid, int nt) {
+  if (M < 4) return;  // M = 1, 2: identity
+  const int lg = 31 - __clz(M);
+  for (int i = tid; i < M; i += nt) {
+    const int rv = (int)(__brev((unsigned)i) >> (32 - lg));
+    if (i < rv) {
+      const double2 t = buf[i];
+      buf[i] = buf[rv];
+      buf[rv] = t;
+    }
+  }
+  __syncthreads();
+}
+
+// U[j] = sum_k src[k] exp(+2 pi i jk / r), j,k < r.
+//   power-of-two r (M == 0): in place in `A` (src must be A).
+//   otherwise Bluestein: src may be A itself or another buffer; the result lands in A[0..r) and
+//   A[r..M) is clobbered.  Caller synchronised before; result visible to all threads on return.
+__device__ void idft_r(double2* A, const double2* src, int r, int M, const double2* __restrict__ hhat,
+                       const Roots& W, const double2* __restrict__ tw, int twn, int tid, int nt) {
+  if (M == 0) {  // r is a power of two
+    fft_dif<true>(A, r, tw, twn, tid, nt);
+    bitrev_permute(A, r, tid, nt);
+    return;
+  }
+  const int two_r = 2 * r;
+  // chirp c[k] = exp(i pi k^2 / r) = W(2 (k^2 mod 2r))
+  for (int k = tid; k < M; k += nt) {
+    double2 v = make_double2(0.0, 0.0);
+    if (k < r) {
+      const int q = (int)(((long long)k * k) % two_r);
+      v = cmul(src[k], W(2 * q));
+    }
+    A[k] = v;
+  }
+  __syncthreads();
+  fft_dif<false>(A, M, tw, twn, tid, nt);
+  for (int k = tid; k < M; k += nt) A[k] = cmul(A[k], __ldg(&hhat[k]));
+  __syncthreads();
+  fft_dit<true>(A, M, tw, twn, tid, nt);
+  for (int k = tid; k < r; k += nt) {
+    const int q = (int)(((long long)k * k) % two_r);
+    A[k] = cmul(A[k], W(2 * q));
+  }
+  __syncthreads();
+}
+
+// Shared-memory carve-up of one CTA.
+//   A  : max(Mmax, 2 rmax + 2) complex — spectrum X[0..2r], then u|v, then the Bluestein work array
+//   B  : rmax complex, only for Bluestein classes (parks v / Uhat while A is the work array)
+struct SmemLayout {
+  double2* A;
+  double2* B;
+  double2* hi;    // rmax*4/64 + 2
+  double2* lo;    // 64
+  double2* part;  // nthreads (fold scratch)
+};
+__host__ __device__ __forceinline__ int size_A(int rmax, int Mmax) {
+  return Mmax > 2 * rmax + 2 ? Mmax : 2 * rmax + 2;
+}
+__device__ __forceinline__ SmemLayout carve(unsigned char* base, int rmax, int Mmax, int nt) {
+  SmemLayout s;
+  double2* p = reinterpret_cast<double2*>(base);
+  s.A = p;
+  p += size_A(rmax, Mmax);
+  s.B = p;
+  p += (Mmax > 0 ? rmax : 0);
+  s.hi = p;
+  p += (rmax * 4) / 64 + 2;
+  s.lo = p;
+  p += 64;
+  s.part = p;
+  return s;
+}
+size_t smem_bytes(int rmax, int Mmax, int nt) {
+  return sizeof(double2) * ((size_t)size_A(rmax, Mmax) + (Mmax > 0 ? rmax : 0) + (rmax * 4) / 64 + 2 + 64 + nt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// leg2map
+// ------------------------------------------------------------------------------------------------
+__global__ void k_leg2map(const RingDesc* __restrict__ desc, int first, const double2* __restrict__ leg,
+                          double* __restrict__ map, int64_t map_cstride, int64_t nm, int64_t nring,
+                          const double2* __restrict__ tw, int twn, const double2* __restrict__ hhat_all,
+                          int rmax, int Mmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const RingDesc d = desc[first + blockIdx.x];
+  const int comp = blockIdx.y;
+  const SmemLayout S = carve(smem_raw, rmax, Mmax, nt);
+  const int n = d.nphi, r = d.r, N = 2 * r;
+  const int mmax = (int)nm - 1;
+  const double2* row = leg + ((int64_t)comp * nring + d.ir) * nm;
+  const Roots W{S.hi, S.lo};
+
+  build_roots(S.hi, S.lo, n, tid, nt);
+
+  // ---- phase shift + alias fold: X[k], k = 0..N ----
+  {
+    const int K = N + 1;
+    const int G = (K < nt) ? nt / K : 1;
+    for (int idx = tid; idx < K * G; idx += nt) {
+      const int k = idx % K, g = idx / K;
+      double ar = 0.0, ai = 0.0;
+      if (k == 0) {
+        if (g == 0) ar = row[0].x;  // c_0 = 1, only Re(leg[0]) enters
+        for (long long m = (long long)(g + 1) * n; m <= mmax; m += (long long)G * n) {
+          const double2 t = cmul(row[m], phase((int)m, d.phi0));
+          ar += 2.0 * t.x;
+        }
+      } else {
+        for (long long m = k + (long long)g * n; m <= mmax; m += (long long)G * n) {
+          const double2 t = cmul(row[m], phase((int)m, d.phi0));
+          ar += t.x;
+          ai += t.y;
+        }
+        for (long long m = (long long)(g + 1) * n - k; m <= mmax; m += (long long)G * n) {
+          const double2 t = cmul(row[m], phase((int)m, d.phi0));
+          ar += t.x;
+          ai -= t.y;
+        }
+      }
+      if (G == 1)
+        S.A[k] = make_double2(ar, ai);
+      else
+        S.part[idx] = make_double2(ar, ai);
+    }
+    if (G > 1) {
+      __syncthreads();
+      for (int k = tid; k < K; k += nt) {
+        double ar = 0.0, ai = 0.0;
+        for (int g = 0; g < G; ++g) {
+          ar += S.part[g * K + k].x;
+          ai += S.part[g * K + k].y;
+        }
+        S.A[k] = make_double2(ar, ai);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- X -> Zc (in place, pairs k <-> N-k) ----
+  for (int k = tid; k <= r; k += nt) {
+    if (k == 0) {
+      const double x0 = S.A[0].x, xn = S.A[N].x;
+      S.A[0] = make_double2(x0 + xn, x0 - xn);
+    } else if (k == r) {
+      const double2 a = S.A[r];
+      S.A[r] = make_double2(2.0 * a.x, -2.0 * a.y);
+    } else {
+      const double2 A = S.A[k], B = cconj(S.A[N - k]);
+      const double2 Pp = cadd(A, B);
+      const double2 D = cmul(csub(A, B), W(k));
+      const double2 Q = make_double2(-D.y, D.x);  // i * w^k (A - B)
+      S.A[k] = cadd(Pp, Q);
+      S.A[N - k] = make_double2(Pp.x - Q.x, -(Pp.y - Q.y));  // conj(P) - conj(Q) = conj(P - Q)
+    }
+  }
+  __syncthreads();
+  // ---- Zc -> u | v (in place) ----
+  for (int k = tid; k < r; k += nt) {
+    const double2 a = S.A[k], b = S.A[k + r];
+    S.A[k] = cadd(a, b);
+    S.A[k + r] = cmul(csub(a, b), W(2 * k));
+  }
+  __syncthreads();
+
+  const double2* hhat = d.hoff >= 0 ? hhat_all + d.hoff : nullptr;
+  double* out = map + (int64_t)comp * map_cstride + d.pixoff;
+  const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (d.M == 0) {
+    // power-of-two r: both halves transformed in place, one fully coalesced store
+    idft_r(S.A, S.A, r, 0, nullptr, W, tw, twn, tid, nt);
+    idft_r(S.A + r, S.A + r, r, 0, nullptr, W, tw, twn, tid, nt);
+    // ---- pixels: x[4j..4j+3] = Re U[j], Im U[j], Re V[j], Im V[j] ----
+    if (al16) {
+      double2* out2 = reinterpret_cast<double2*>(out);
+      for (int t = tid; t < N; t += nt) out2[t] = (t & 1) ? S.A[r + (t >> 1)] : S.A[t >> 1];
+    } else {
+      for (int t = tid; t < N; t += nt) {
+        const double2 v = (t & 1) ? S.A[r + (t >> 1)] : S.A[t >> 1];
+        out[2 * t] = v.x;
+        out[2 * t + 1] = v.y;
+      }
+    }
+  } else {
+    // Bluestein: A becomes the work array, v waits in B.  U and V are stored as interleaved 16-byte
+    // pieces (the two stores of a 32-byte sector meet in L2).
+    for (int k = tid; k < r; k += nt) S.B[k] = S.A[k + r];
+    __syncthreads();
+    for (int half = 0; half < 2; ++half) {
+      idft_r(S.A, half == 0 ? S.A : S.B, r, d.M, hhat, W, tw, twn, tid, nt);
+      if (al16) {
+        double2* out2 = reinterpret_cast<double2*>(out);
+        for (int j = tid; j < r; j += nt) out2[2 * j + half] = S.A[j];
+      } else {
+        for (int j = tid; j < r; j += nt) {
+          out[4 * j + 2 * half] = S.A[j].x;
+          out[4 * j + 2 * half + 1] = S.A[j].y;
+        }
+      }
+      __syncthreads();  // A is reused as the work array of the second half
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// map2leg
+// ------------------------------------------------------------------------------------------------
+__global__ void k_map2leg(const RingDesc* __restrict__ desc, int first, const double* __restrict__ map,
+                          int64_t map_cstride, double2* __restrict__ leg, int64_t nm, int64_t nring,
+                          const double2* __restrict__ tw, int twn, const double2* __restrict__ hhat_all,
+                          int rmax, int Mmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const RingDesc d = desc[first + blockIdx.x];
+  const int comp = blockIdx.y;
+  const SmemLayout S = carve(smem_raw, rmax, Mmax, nt);
+  const int n = d.nphi, r = d.r, N = 2 * r;
+  const int mmax = (int)nm - 1;
+  double2* row = leg + ((int64_t)comp * nring + d.ir) * nm;
+  const Roots W{S.hi, S.lo};
+
+  build_roots(S.hi, S.lo, n, tid, nt);
+
+  // ---- pixels -> conj(u) | conj(v) ;  u[j] = x[4j] + i x[4j+1], v[j] = x[4j+2] + i x[4j+3] ----
+  const double* in = map + (int64_t)comp * map_cstride + d.pixoff;
+  const bool al16 = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  double2* vdst = d.M == 0 ? S.A + r : S.B;  // Bluestein: v parks in B while A is the work array
+  if (al16) {
+    const double2* in2 = reinterpret_cast<const double2*>(in);
+    for (int t = tid; t < N; t += nt) {
+      const double2 v = in2[t];
+      ((t & 1) ? vdst : S.A)[t >> 1] = make_double2(v.x, -v.y);
+    }
+  } else {
+    for (int t = tid; t < N; t += nt)
+      ((t & 1) ? vdst : S.A)[t >> 1] = make_double2(in[2 * t], -in[2 * t + 1]);
+  }
+  __syncthreads();
+
+  const double2* hhat = d.hoff >= 0 ? hhat_all + d.hoff : nullptr;
+  if (d.M == 0) {
+    idft_r(S.A, S.A, r, 0, nullptr, W, tw, twn, tid, nt);          // = conj(Uhat)
+    idft_r(S.A + r, S.A + r, r, 0, nullptr, W, tw, twn, tid, nt);  // = conj(Vhat)
+  } else {
+    idft_r(S.A, S.A, r, d.M, hhat, W, tw, twn, tid, nt);  // conj(Uhat) in A[0..r)
+    for (int k = tid; k < r; k += nt) {                   // swap: conj(Uhat) -> B, conj(v) -> A
+      const double2 t = S.A[k];
+      S.A[k] = S.B[k];
+      S.B[k] = t;
+    }
+    __syncthreads();
+    idft_r(S.A, S.A, r, d.M, hhat, W, tw, twn, tid, nt);  // conj(Vhat) in A[0..r)
+    for (int k = tid; k < r; k += nt) {                   // A[0..r) = conj(Uhat), A[r..2r) = conj(Vhat)
+      const double2 vh = S.A[k];
+      S.A[k] = S.B[k];
+      S.A[k + r] = vh;
+    }
+    __syncthreads();
+  }
+
+  // ---- Z[k] = Uhat[k] + conj(w)^{2k} Vhat[k],  Z[k+r] = Uhat[k] - ...  (in place) ----
+  for (int k = tid; k < r; k += nt) {
+    const double2 uh = cconj(S.A[k]), vh = cconj(S.A[k + r]);
+    const double2 t = cmulc(vh, W(2 * k));
+    S.A[k] = cadd(uh, t);
+    S.A[k + r] = csub(uh, t);
+  }
+  __syncthreads();
+  // ---- Z -> X[0..N] (pairs k <-> N-k) ----
+  for (int k = tid; k <= r; k += nt) {
+    if (k == 0) {
+      const double2 z = S.A[0];
+      S.A[0] = make_double2(z.x + z.y, 0.0);
+      S.A[N] = make_double2(z.x - z.y, 0.0);
+    } else if (k == r) {
+      S.A[r] = cconj(S.A[r]);
+    } else {
+      const double2 A = S.A[k], B = cconj(S.A[N - k]);
+      const double2 Pp = make_double2(0.5 * (A.x + B.x), 0.5 * (A.y + B.y));
+      const double2 D = cmulc(csub(A, B), W(k));             // conj(w^k) (A - B)
+      const double2 Q = make_double2(0.5 * D.y, -0.5 * D.x);  // -i/2 * D
+      S.A[k] = cadd(Pp, Q);
+      S.A[N - k] = make_double2(Pp.x - Q.x, -(Pp.y - Q.y));
+    }
+  }
+  __syncthreads();
+  // ---- un-alias + phase shift: leg[m] = exp(-i m phi0) Xt[m mod n] ----
+  for (int m = tid; m <= mmax; m += nt) {
+    const int k = m % n;
+    const double2 v = (k <= N) ? S.A[k] : cconj(S.A[n - k]);
+    row[m] = cmulc(v, phase(m, d.phi0));
+  }
+}
+
+// chirp spectrum of one r:  hhat = DIF_forward(h) / M,  h[d] = conj(c[|d|]) circularly, |d| < r
+__global__ void k_build_hhat(const int* __restrict__ rs, const int* __restrict__ Ms,
+                             const int64_t* __restrict__ hoffs, double2* __restrict__ hhat_all,
+                             const double2* __restrict__ tw, int twn, int rmax, int Mmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const SmemLayout S = carve(smem_raw, rmax, Mmax, nt);
+  const int r = rs[blockIdx.x], M = Ms[blockIdx.x];
+  const int n = 4 * r;
+  const Roots W{S.hi, S.lo};
+  build_roots(S.hi, S.lo, n, tid, nt);
+  __syncthreads();
+  const double inv = 1.0 / (double)M;
+  for (int k = tid; k < M; k += nt) {
+    int dd = -1;
+    if (k < r)
+      dd = k;
+    else if (k > M - r)
+      dd = M - k;
+    double2 v = make_double2(0.0, 0.0);
+    if (dd >= 0) {
+      const int q = (int)(((long long)dd * dd) % (2 * r));
+      const double2 c = W(2 * q);
+      v = make_double2(c.x * inv, -c.y * inv);
+    }
+    S.A[k] = v;
+  }
+  __syncthreads();
+  fft_dif<false>(S.A, M, tw, twn, tid, nt);
+  double2* out = hhat_all + hoffs[blockIdx.x];
+  for (int k = tid; k < M; k += nt) out[k] = S.A[k];
+}
+
+int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, const int64_t* ringstart,
+                    int64_t nm, cudaStream_t stream) {
+  nring_ = nring;
+  nm_ = nm;
+  npix_ = 0;
+  desc_.clear();
+  classes_.clear();
+  HP_REQUIRE(nm >= 1 && nm < (1ll << 30), HPSHT_ERR_ARG, "invalid nm");
+  std::map<int, int64_t> hoff_of_r;
+  std::vector<int> rs, Ms;
+  std::vector<int64_t> hoffs;
+  int64_t htotal = 0;
+  int twn = 2;
+  for (int64_t i = 0; i < nring; ++i) {
+    const int64_t n = nphi[i];
+    HP_REQUIRE(n >= 4 && n % 4 == 0, HPSHT_ERR_UNSUPPORTED,
+               "ring length must be a positive multiple of 4 (HEALPix rings always are)");
+    HP_REQUIRE(n / 4 <= 4096, HPSHT_ERR_UNSUPPORTED,
+               "ring length > 16384 (nside > 4096) needs the multi-CTA FFT path, not built yet");
+    npix_ += n;
+    RingDesc d;
+    d.pixoff = ringstart[i];
+    d.phi0 = phi0[i];
+    d.ir = (int)i;
+    d.nphi = (int)n;
+    d.r = (int)(n / 4);
+    const bool pow2 = (d.r & (d.r - 1)) == 0;
+    if (pow2) {
+      d.M = 0;
+      d.hoff = -1;
+      twn = std::max(twn, d.r);
+    } else {
+      d.M = next_pow2(2 * d.r - 1);
+      twn = std::max(twn, d.M);
+      auto it = hoff_of_r.find(d.r);
+      if (it == hoff_of_r.end()) {
+        hoff_of_r[d.r] = htotal;
+        rs.push_back(d.r);
+        Ms.push_back(d.M);
+        hoffs.push_back(htotal);
+        d.hoff = htotal;
+        htotal += d.M;
+      } else {
+        d.hoff = it->second;
+      }
+    }
+    desc_.push_back(d);
+  }
+  twn_ = twn;
+  // twiddle table exp(-2 pi i k / twn), k < twn/2, in long double on the host
+  {
+    std::vector<double> tw((size_t)std::max(1, twn / 2) * 2);
+    const long double PI = 3.14159265358979323846264338327950288419716939937510L;
+    for (int k = 0; k < std::max(1, twn / 2); ++k) {
+      const long double a = -2.0L * PI * (long double)k / (long double)twn;
+      tw[2 * (size_t)k] = (double)cosl(a);
+      tw[2 * (size_t)k + 1] = (double)sinl(a);
+    }
+    d_tw_.upload(tw.data(), tw.size(), stream);
+  }
+  // size classes: big CTAs for big rings; Bluestein rings need the extra work buffer
+  std::stable_sort(desc_.begin(), desc_.end(), [](const RingDesc& a, const RingDesc& b) {
+    const int ca = (a.M != 0) ? std::max(a.M, 2 * a.r) : 2 * a.r;
+    const int cb = (b.M != 0) ? std::max(b.M, 2 * b.r) : 2 * b.r;
+    if ((a.M != 0) != (b.M != 0)) return (a.M != 0) > (b.M != 0);
+    return ca > cb;
+  });
+  auto bucket = [](const RingDesc& d) {
+    const int work = d.M ? d.M : d.r;
+    const int b = work > 2048 ? 3 : (work > 512 ? 2 : (work > 64 ? 1 : 0));
+    return (d.M ? 4 : 0) + b;
+  };
+  for (size_t i = 0; i < desc_.size();) {
+    size_t j = i;
+    Class c;
+    c.first = (int)i;
+    const int bk = bucket(desc_[i]);
+    while (j < desc_.size() && bucket(desc_[j]) == bk) {
+      c.rmax = std::max(c.rmax, desc_[j].r);
+      c.Mmax = std::max(c.Mmax, desc_[j].M);
+      ++j;
+    }
+    c.count = (int)(j - i);
+    const int work = std::max(c.Mmax, c.rmax);
+    c.threads = work > 2048 ? 512 : (work > 512 ? 256 : (work > 64 ? 128 : 64));
+    c.smem = smem_bytes(c.rmax, c.Mmax, c.threads);
+    classes_.push_back(c);
+    i = j;
+  }
+  d_desc_.upload(desc_.data(), desc_.size(), stream);
+  size_t max_smem = 0;
+  for (auto& c : classes_) max_smem = std::max(max_smem, c.smem);
+  HP_REQUIRE(max_smem <= 227 * 1024, HPSHT_ERR_UNSUPPORTED, "ring too long for the in-smem FFT");
+  HP_CUDA(cudaFuncSetAttribute(k_leg2map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  HP_CUDA(cudaFuncSetAttribute(k_map2leg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  // chirp spectra
+  d_hhat_.alloc((size_t)std::max<int64_t>(htotal, 1) * 2);
+  if (!rs.empty()) {
+    DevBuf<int> d_rs, d_Ms;
+    DevBuf<int64_t> d_hoffs;
+    d_rs.upload(rs.data(), rs.size(), stream);
+    d_Ms.upload(Ms.data(), Ms.size(), stream);
+    d_hoffs.upload(hoffs.data(), hoffs.size(), stream);
+    int rmax = 0, Mmax = 0;
+    for (size_t i = 0; i < rs.size(); ++i) {
+      rmax = std::max(rmax, rs[i]);
+      Mmax = std::max(Mmax, Ms[i]);
+    }
+    const int nt = 256;
+    const size_t sm = smem_bytes(rmax, Mmax, nt);
+    HP_CUDA(cudaFuncSetAttribute(k_build_hhat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_build_hhat<<<(unsigned)rs.size(), nt, sm, stream>>>(
+        d_rs.p, d_Ms.p, d_hoffs.p, reinterpret_cast<double2*>(d_hhat_.p),
+        reinterpret_cast<const double2*>(d_tw_.p), twn_, rmax, Mmax);
+    HP_CUDA(cudaGetLastError());
+    HP_CUDA(cudaStreamSynchronize(stream));
+  }
+  HP_CUDA(cudaStreamSynchronize(stream));
+}
+
+void RingFFT::leg2map(const double* d_leg, double* d_map, int64_t map_cstride, int ncomp,
+                      cudaStream_t stream) {
+  for (const Class& c : classes_) {
+    dim3 grid((unsigned)c.count, (unsigned)ncomp);
+    k_leg2map<<<grid, c.threads, c.smem, stream>>>(
+        d_desc_.p, c.first, reinterpret_cast<const double2*>(d_leg), d_map, map_cstride, nm_, nring_,
+        reinterpret_cast<const double2*>(d_tw_.p), twn_, reinterpret_cast<const double2*>(d_hhat_.p),
+        c.rmax, c.Mmax);
+    ++launches_;
+  }
+  HP_CUDA(cudaGetLastError());
+}
+
+void RingFFT::map2leg(const double* d_map, int64_t map_cstride, double* d_leg, int ncomp,
+                      cudaStream_t stream) {
+  for (const Class& c : classes_) {
+    dim3 grid((unsigned)c.count, (unsigned)ncomp);
+    k_map2leg<<<grid, c.threads, c.smem, stream>>>(
+        d_desc_.p, c.first, d_map, map_cstride, reinterpret_cast<double2*>(d_leg), nm_, nring_,
+        reinterpret_cast<const double2*>(d_tw_.p), twn_, reinterpret_cast<const double2*>(d_hhat_.p),
+        c.rmax, c.Mmax);
+    ++launches_;
+  }
+  HP_CUDA(cudaGetLastError());
+}
+
+}  // namespace hpsht

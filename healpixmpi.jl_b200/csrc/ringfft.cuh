@@ -1,0 +1,65 @@
+// ringfft.cuh — host interface of the per-ring FFT stage (ringfft.cu).
+//
+// Replaces Ducc0.Sht.leg2map! (reference src/sht.jl:93) and Ducc0.Sht.map2leg! (src/sht.jl:169):
+// per ring, phase shift exp(+-i m phi0), alias fold of m = 0..mmax onto the ring length, and a real
+// FFT of length nphi (unnormalised).  leg layout is the reference's map-side one:
+// leg[(comp*nring + ir)*nm + m]; map[comp*map_cstride + ringstart[ir] + j].
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <vector>
+
+#include "common.hpp"
+
+namespace hpsht {
+
+struct RingDesc {
+  int64_t pixoff;   // 0-based offset of the ring's first pixel in one map component
+  int64_t hoff;     // offset (complex elements) of the ring's chirp spectrum, -1 for power-of-two r
+  double phi0;
+  int ir;           // ring slot in the leg array
+  int nphi;         // ring length n = 4 r
+  int r;
+  int M;            // Bluestein convolution length (power of two >= 2r-1), 0 for power-of-two r
+};
+
+class RingFFT {
+ public:
+  RingFFT() = default;
+  ~RingFFT() = default;
+  RingFFT(const RingFFT&) = delete;
+  RingFFT& operator=(const RingFFT&) = delete;
+
+  void setup(int64_t nring, const int64_t* nphi, const double* phi0, const int64_t* ringstart,
+             int64_t nm, cudaStream_t stream);
+  // device pointers
+  void leg2map(const double* d_leg, double* d_map, int64_t map_cstride, int ncomp,
+               cudaStream_t stream);
+  void map2leg(const double* d_map, int64_t map_cstride, double* d_leg, int ncomp,
+               cudaStream_t stream);
+
+  int64_t launches() const { return launches_; }
+  void reset_launches() { launches_ = 0; }
+  // algorithmic HBM bytes of one component, one direction: 16*nm*nring + 8*npix
+  double algorithmic_bytes() const { return 16.0 * (double)nm_ * (double)nring_ + 8.0 * (double)npix_; }
+
+ private:
+  struct Class {
+    int first = 0, count = 0;  // range in the sorted descriptor array
+    int threads = 0;
+    size_t smem = 0;
+    int rmax = 0, Mmax = 0;
+  };
+  int64_t nring_ = 0, nm_ = 0, npix_ = 0;
+  int64_t launches_ = 0;
+  int twn_ = 0;
+  std::vector<RingDesc> desc_;
+  std::vector<Class> classes_;
+  DevBuf<RingDesc> d_desc_;
+  DevBuf<double> d_tw_;     // exp(-2 pi i k / twn), k < twn/2 (re,im)
+  DevBuf<double> d_hhat_;   // chirp spectra
+};
+
+}  // namespace hpsht

@@ -125,6 +125,11 @@ int hpsht_nccl_unique_id(unsigned char id[HPSHT_NCCL_ID_BYTES]);
    max_ncomp (1 or 2) sizes the internal leg buffers.                                    */
 int hpsht_plan_create(hpsht_plan** plan, int64_t nside, int64_t lmax, int rank, int n_ranks,
                       const unsigned char* nccl_id, int device, int max_ncomp);
+/* Optional: override the internally derived ring geometry with the caller's own doubles
+   (d_map.info.thetatot [nring_tot] and d_map.info.phi0 [nring_loc], src/map.jl:189-196), so the
+   plan sees bit-identical inputs to what the reference hands Ducc0.  Either may be NULL.
+   Must be called before the first transform.                                            */
+int hpsht_plan_set_geometry(hpsht_plan* plan, const double* thetatot, const double* phi0_loc);
 int hpsht_plan_destroy(hpsht_plan* plan);
 
 /* Sizes and descriptor arrays of this rank's shard (so callers can cross-check them
@@ -144,8 +149,8 @@ int hpsht_adjoint_alm2map(hpsht_plan* plan, const double* map, double* alm, int 
                           int nthreads);
 
 /* Per-stage device times (ms, CUDA events) of the most recent fused call on this plan:
-   [0] total, [1] alm prep/post, [2] Legendre, [3] all-to-all (+pack/unpack transposes),
-   [4] ring FFT, [5] H2D, [6] D2H.                                                       */
+   [0] total, [1] the Legendre recurrence kernel alone, [2] whole Legendre stage (with the O(nalm)
+   prep / reduce / post kernels), [3] all-to-all (+pack/unpack), [4] ring FFT, [5] H2D, [6] D2H.                                                       */
 #define HPSHT_NTIMES 8
 int hpsht_plan_timings(const hpsht_plan* plan, double ms[HPSHT_NTIMES]);
 /* Number of kernel launches issued by the most recent fused call.                       */
@@ -159,6 +164,9 @@ int hpsht_plan_legendre_steps(const hpsht_plan* plan, int spin, double* steps_cu
    resident.                                                                 */
 int hpsht_device_malloc(void** dptr, size_t bytes);
 int hpsht_device_free(void* dptr);
+/* page-locked host memory (fast H2D/D2H for host-pointer calls) */
+int hpsht_host_malloc(void** hptr, size_t bytes);
+int hpsht_host_free(void* hptr);
 int hpsht_memcpy_h2d(void* dptr, const void* hptr, size_t bytes);
 int hpsht_memcpy_d2h(void* hptr, const void* dptr, size_t bytes);
 int hpsht_device_synchronize(void);
