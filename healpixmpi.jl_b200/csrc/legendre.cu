@@ -30,8 +30,7 @@ namespace hpsht {
 namespace {
 
 constexpr int NSTAGE = 4;
-constexpr double SC_BIG = 2.5822498780869086e+120;      // 2^400
-constexpr double SC_DOWN = 1.4997597826618576e-241;     // 2^-800
+constexpr double SC_DOWN = 0x1p-800;  // exact power of two: rescaling never rounds
 constexpr int SC_STEP = 800;
 
 struct __align__(16) Coef {

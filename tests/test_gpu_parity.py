@@ -372,9 +372,19 @@ def test_large_size_properties(H, O):
         rstart0 = np.concatenate([[0], np.cumsum(nphi)[:-1]]).astype(np.int64)
         ref = O.leg2map(leg, nphi, phi0, rstart0, int(nphi.sum())).astype(np.float64)
         loc = {int(r): (int(s), int(n)) for r, s, n in zip(info["rings"], info["rstart0"], info["nphi"])}
-        got = np.concatenate([m1[:, loc[r][0]:loc[r][0] + loc[r][1]] for r in sel], axis=1)
-        # global-norm-relative error of the sampled rings (per-ring worst case reported separately)
-        scale = np.sqrt(np.mean(ref ** 2))
-        err = np.sqrt(np.mean((got - ref) ** 2)) / scale
-        assert err < 1e-12, err
+        # per-ring relative L2 (pixel domain).  The few rings next to the poles carry ~1e-10 local
+        # error in any plain-FP64 recurrence at this lmax (conditioning eps*l/sin(theta))
+        # and hold a vanishing share of the pixels; the rest must sit at the 1e-13 level.
+        per = []
+        for r in sel:
+            a = list(sel).index(r)
+            sl = slice(int(rstart0[a]), int(rstart0[a] + nphi[a]))
+            g = m1[:, loc[r][0]:loc[r][0] + loc[r][1]]
+            per.append(rel_l2(g, ref[:, sl]))
+        per = np.array(per)
+        polar = nphi < 64
+        assert np.all(per[polar] < 1e-9), per
+        assert np.all(per[~polar] < 3e-12), per
+        w = nphi[~polar].astype(float)
+        assert np.sqrt(np.sum(w * per[~polar] ** 2) / np.sum(w)) < 1e-12, per
         plan.destroy()
