@@ -7,7 +7,7 @@
 //   * every consumer thread owns R ring pairs and evaluates the scaled recurrence on the fly in
 //     registers (no Plm table); north/south symmetry gives both rings of a pair from one recurrence;
 //   * the per-m coefficient stream (recurrence coefficients + prepared alm) is the only data the
-//     inner loop reads; a dedicated producer warp moves it global->shared with 1-D TMA bulk copies
+//     inner loop reads; thread 0 of the CTA moves it global->shared with 1-D TMA bulk copies
 //     (cp.async.bulk ... mbarrier::complete_tx) through a 4-stage full/empty mbarrier ring, and the
 //     consumers read it as warp-broadcast LDS.128;
 //   * dynamic range: value = lam * 2^(800*sc), sc <= 0 tracked per ring; a warp whose lanes are all
@@ -83,41 +83,53 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// base^n (n >= 0) as mant * 2^e, mant in [0.5, 1)
+// x = m * 2^e with |m| in [0.5, 1): frexp for NORMAL non-zero doubles, done on the integer pipe so
+// that the start-value computation does not compete with the recurrence for the FP64 pipe.
+__device__ __forceinline__ void split_normal(double x, double& m, int& e) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  e = ((hi >> 20) & 0x7ff) - 1022;
+  m = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, lo);
+}
+// 2^k for -1022 <= k <= 1023
+__device__ __forceinline__ double pow2i(int k) { return __hiloint2double((k + 1023) << 20, 0); }
+
+// base^n (n >= 0) as mant * 2^e, mant in [0.5, 1); base must be 0 or a normal double
 __device__ __forceinline__ void pow_scaled(double base, int n, double& mant, int& e) {
-  int be;
-  double b = frexp(base, &be);
   mant = 1.0;
   e = 0;
+  if (n == 0) return;
+  if (base == 0.0) {
+    mant = 0.0;
+    return;
+  }
+  int be;
+  double b;
+  split_normal(base, b, be);
   while (n > 0) {
     if (n & 1) {
-      mant *= b;
-      e += be;
       int t;
-      mant = frexp(mant, &t);
-      e += t;
+      split_normal(mant * b, mant, t);
+      e += be + t;
     }
-    b *= b;
-    be *= 2;
     int t;
-    b = frexp(b, &t);
-    be += t;
+    split_normal(b * b, b, t);
+    be = 2 * be + t;
     n >>= 1;
   }
 }
 // v * 2^e -> lam * 2^(800 sc), sc <= 0, |lam| in [2^-400, 2^400) when sc < 0
 __device__ __forceinline__ void to_scaled(double v, int e, double& lam, int& sc) {
-  if (v == 0.0) {
+  if (v == 0.0 || fabs(v) < 1e-290) {  // zero (or hopelessly small: treated as zero)
     lam = 0.0;
     sc = 0;
     return;
   }
   int t;
-  v = frexp(v, &t);
+  split_normal(v, v, t);
   e += t;
   sc = (e >= -400) ? 0 : -((-e - 400 + SC_STEP - 1) / SC_STEP);
-  int ee = e - SC_STEP * sc;
-  lam = (ee < -1070) ? 0.0 : ldexp(v, ee);
+  const int ee = e - SC_STEP * sc;  // in (-400, 400] when sc < 0; may be very negative when sc == 0
+  lam = (ee < -1000) ? 0.0 : v * pow2i(ee);
 }
 __device__ __forceinline__ bool is_big(double v) {
   // |v| > 2^400  <=>  biased exponent field > 1023+400 (ties at exactly 2^400 are irrelevant)
@@ -156,34 +168,29 @@ struct LegParams {
 };
 
 // ------------------------------------------------------------------------------------------------
-// producer warp: streams `nchunks` chunks of coef (and optionally the alm stream) into the ring
+// producer side of the coefficient pipeline.  Thread 0 of the CTA issues the 1-D TMA bulk copies of
+// chunk `cn` (counted over the whole CTA lifetime; the per-m stream is replayed once per tile in the
+// adjoint) into stage cn % NSTAGE, after every consumer warp released that stage.
 // ------------------------------------------------------------------------------------------------
 template <bool WITH_STREAM>
-__device__ __forceinline__ void producer_loop(int nchunks, int nrepeat, const double* gcoef,
-                                              const double* gstrm, Coef (*s_coef)[LEG_CHUNK],
-                                              Strm (*s_strm)[LEG_CHUNK], uint64_t* full,
-                                              uint64_t* empty) {
-  int cg = 0;  // position in the stage ring (the same stream is replayed once per tile)
-  for (int rep = 0; rep < nrepeat; ++rep) {
-    for (int c = 0; c < nchunks; ++c, ++cg) {
-      const int st = cg % NSTAGE;
-      if (cg >= NSTAGE) mbar_wait(&empty[st], ((cg / NSTAGE) - 1) & 1);
-      const uint32_t bytes = LEG_CHUNK * sizeof(Coef) + (WITH_STREAM ? LEG_CHUNK * sizeof(Strm) : 0);
-      mbar_arrive_expect_tx(&full[st], bytes);
-      tma_load_1d(&s_coef[st][0], gcoef + (size_t)c * LEG_CHUNK * 2, LEG_CHUNK * sizeof(Coef),
-                  &full[st]);
-      if (WITH_STREAM)
-        tma_load_1d(&s_strm[st][0], gstrm + (size_t)c * LEG_CHUNK * 4, LEG_CHUNK * sizeof(Strm),
-                    &full[st]);
-    }
-  }
+__device__ __forceinline__ void issue_chunk(int cn, int nchunks, const double* gcoef, const double* gstrm,
+                                            Coef (*s_coef)[LEG_CHUNK], Strm (*s_strm)[LEG_CHUNK],
+                                            uint64_t* full, uint64_t* empty) {
+  const int st = cn % NSTAGE;
+  const int c = cn % nchunks;
+  if (cn >= NSTAGE) mbar_wait(&empty[st], ((cn / NSTAGE) - 1) & 1);
+  const uint32_t bytes = LEG_CHUNK * sizeof(Coef) + (WITH_STREAM ? LEG_CHUNK * sizeof(Strm) : 0);
+  mbar_arrive_expect_tx(&full[st], bytes);
+  tma_load_1d(&s_coef[st][0], gcoef + (size_t)c * LEG_CHUNK * 2, LEG_CHUNK * sizeof(Coef), &full[st]);
+  if (WITH_STREAM)
+    tma_load_1d(&s_strm[st][0], gstrm + (size_t)c * LEG_CHUNK * 4, LEG_CHUNK * sizeof(Strm), &full[st]);
 }
 
 // ================================================================================================
 // spin 0 synthesis:  leg_N/S = sum_n p_n A_n  +-  x sum_n p_n B_n
 // ================================================================================================
 template <int R, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
+__global__ void __launch_bounds__(NW * 32) k_alm2leg_s0(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ Strm s_strm[NSTAGE][LEG_CHUNK];
   __shared__ __align__(8) uint64_t s_full[NSTAGE];
@@ -206,12 +213,11 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
   }
   __syncthreads();
 
-  if (warp == NW) {  // ---------------- producer warp ----------------
-    if (lane == 0)
-      producer_loop<true>(nchunks, 1, P.coef + (size_t)P.off[mi] * 2, P.stream + (size_t)P.off[mi] * 4,
-                          s_coef, s_strm, s_full, s_empty);
-    return;
-  }
+  const double* gcoef = P.coef + (size_t)P.off[mi] * 2;
+  const double* gstrm = P.stream + (size_t)P.off[mi] * 4;
+  if (threadIdx.x == 0)
+    for (int cn = 0; cn < NSTAGE - 1 && cn < nchunks; ++cn)
+      issue_chunk<true>(cn, nchunks, gcoef, gstrm, s_coef, s_strm, s_full, s_empty);
 
   // ---------------- consumer warps ----------------
   double csq[R], lam1[R], lam2[R];
@@ -244,6 +250,9 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
 
   for (int c = 0; c < nchunks; ++c) {
     const int st = c % NSTAGE;
+    if (threadIdx.x == 0 && c + NSTAGE - 1 < nchunks)
+      issue_chunk<true>(c + NSTAGE - 1, nchunks, gcoef, gstrm, s_coef, s_strm, s_full, s_empty);
+    __syncwarp();
     mbar_wait(&s_full[st], (c / NSTAGE) & 1);
     if (warp_act) {
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
 //   Q = P+ + P- ; U = -i (P+ - P-)
 // ================================================================================================
 template <int R, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
+__global__ void __launch_bounds__(NW * 32) k_alm2leg_s2(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ Strm s_strm[NSTAGE][LEG_CHUNK];
   __shared__ __align__(8) uint64_t s_full[NSTAGE];
@@ -351,12 +360,11 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
   }
   __syncthreads();
 
-  if (warp == NW) {
-    if (lane == 0)
-      producer_loop<true>(nchunks, 1, P.coef + (size_t)P.off[mi] * 2, P.stream + (size_t)P.off[mi] * 4,
-                          s_coef, s_strm, s_full, s_empty);
-    return;
-  }
+  const double* gcoef = P.coef + (size_t)P.off[mi] * 2;
+  const double* gstrm = P.stream + (size_t)P.off[mi] * 4;
+  if (threadIdx.x == 0)
+    for (int cn = 0; cn < NSTAGE - 1 && cn < nchunks; ++cn)
+      issue_chunk<true>(cn, nchunks, gcoef, gstrm, s_coef, s_strm, s_full, s_empty);
 
   double x[R], lp1[R], lp2[R], lm1[R], lm2[R];
   double pnr[R], pni[R], mnr[R], mni[R];  // P+N, P-N
@@ -398,6 +406,9 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
 
   for (int c = 0; c < nchunks; ++c) {
     const int st = c % NSTAGE;
+    if (threadIdx.x == 0 && c + NSTAGE - 1 < nchunks)
+      issue_chunk<true>(c + NSTAGE - 1, nchunks, gcoef, gstrm, s_coef, s_strm, s_full, s_empty);
+    __syncwarp();
     mbar_wait(&s_full[st], (c / NSTAGE) & 1);
     if (warp_act) {
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
@@ -547,7 +558,7 @@ __device__ __forceinline__ void flush_chunk(const double (*s_red)[LEG_CHUNK * 4]
 // accumulates its own partial sums in global memory (read-modify-write by the same thread, L2
 // resident), so the number of partial buffers per m is the number of items, not of tiles.
 template <int R, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32) k_leg2alm_s0(LegParams P) {
+__global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s0(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ double s_red[2][NW][LEG_CHUNK * 4];
   __shared__ __align__(8) uint64_t s_full[NSTAGE];
@@ -572,12 +583,11 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_leg2alm_s0(LegParams P) {
   }
   __syncthreads();
 
-  if (warp == NW) {
-    if (lane == 0)
-      producer_loop<false>(nchunks, ntile, P.coef + (size_t)P.off[mi] * 2, nullptr, s_coef, nullptr,
-                           s_full, s_empty);
-    return;
-  }
+  const double* gcoef = P.coef + (size_t)P.off[mi] * 2;
+  const int total_chunks = nchunks * ntile;
+  if (threadIdx.x == 0)
+    for (int cn = 0; cn < NSTAGE - 1 && cn < total_chunks; ++cn)
+      issue_chunk<false>(cn, nchunks, gcoef, nullptr, s_coef, nullptr, s_full, s_empty);
 
   const double2* leg = reinterpret_cast<const double2*>(P.leg);
   const double k0 = P.k0[mi];
@@ -632,6 +642,9 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_leg2alm_s0(LegParams P) {
     for (int c = 0; c < nchunks; ++c, ++cg) {
       const int st = cg % NSTAGE;
       double* red = &s_red[cg & 1][warp][0];
+      if (threadIdx.x == 0 && cg + NSTAGE - 1 < total_chunks)
+        issue_chunk<false>(cg + NSTAGE - 1, nchunks, gcoef, nullptr, s_coef, nullptr, s_full, s_empty);
+      __syncwarp();
       mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
       for (int g = 0; g < LEG_CHUNK / LEG_GROUP; ++g) {
@@ -709,7 +722,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_leg2alm_s0(LegParams P) {
 // spin 2 adjoint:  G+_l = sum_pairs [ d+ w+N + (-1)^(l+m) d- w+S ],  G-_l = sum_pairs [ d- w-N + (-1)^(l+m) d+ w-S ]
 //   w+- = legQ +- i legU
 template <int R, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32) k_leg2alm_s2(LegParams P) {
+__global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s2(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ double s_red[2][NW][LEG_CHUNK * 4];
   __shared__ __align__(8) uint64_t s_full[NSTAGE];
@@ -734,12 +747,11 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_leg2alm_s2(LegParams P) {
   }
   __syncthreads();
 
-  if (warp == NW) {
-    if (lane == 0)
-      producer_loop<false>(nchunks, ntile, P.coef + (size_t)P.off[mi] * 2, nullptr, s_coef, nullptr,
-                           s_full, s_empty);
-    return;
-  }
+  const double* gcoef = P.coef + (size_t)P.off[mi] * 2;
+  const int total_chunks = nchunks * ntile;
+  if (threadIdx.x == 0)
+    for (int cn = 0; cn < NSTAGE - 1 && cn < total_chunks; ++cn)
+      issue_chunk<false>(cn, nchunks, gcoef, nullptr, s_coef, nullptr, s_full, s_empty);
 
   const double2* leg = reinterpret_cast<const double2*>(P.leg);
   const double kp = P.k0[mi], km = P.k1[mi];
@@ -828,6 +840,9 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_leg2alm_s2(LegParams P) {
     for (int c = 0; c < nchunks; ++c, ++cg) {
       const int st = cg % NSTAGE;
       double* red = &s_red[cg & 1][warp][0];
+      if (threadIdx.x == 0 && cg + NSTAGE - 1 < total_chunks)
+        issue_chunk<false>(cg + NSTAGE - 1, nchunks, gcoef, nullptr, s_coef, nullptr, s_full, s_empty);
+      __syncwarp();
       mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
       for (int g = 0; g < LEG_CHUNK / LEG_GROUP; ++g) {
@@ -1110,8 +1125,8 @@ namespace {
 // kernel configurations
 constexpr int S0_R = 4, S0_NW = 4;   // spin-0 synthesis: 512 pairs / tile
 constexpr int S2_R = 2, S2_NW = 4;   // spin-2 synthesis: 256 pairs / tile
-constexpr int A0_R = 4, A0_NW = 4;   // spin-0 adjoint:   512 pairs / tile
-constexpr int A2_R = 2, A2_NW = 4;   // spin-2 adjoint:   256 pairs / tile
+constexpr int A0_R = 8, A0_NW = 4;   // spin-0 adjoint:  1024 pairs / tile
+constexpr int A2_R = 4, A2_NW = 4;   // spin-2 adjoint:   512 pairs / tile
 
 // Work list: for every local m (ascending == descending cost; CTAs are handed out in blockIdx
 // order) the active tiles, i.e. those holding at least one pair with mlim >= m.  Pairs are sorted
@@ -1335,7 +1350,7 @@ void LegendreStage::alm2leg(const double* d_alm, int64_t alm_cstride, double* d_
     P.stream = d_stream0_.p;
     if (!items_s0_.empty()) {
       cudaEventRecord(ev0_, stream);
-      k_alm2leg_s0<S0_R, S0_NW><<<(unsigned)items_s0_.size(), (S0_NW + 1) * 32, 0, stream>>>(P);
+      k_alm2leg_s0<S0_R, S0_NW><<<(unsigned)items_s0_.size(), S0_NW * 32, 0, stream>>>(P);
       cudaEventRecord(ev1_, stream);
       ++launches_;
     }
@@ -1359,7 +1374,7 @@ void LegendreStage::alm2leg(const double* d_alm, int64_t alm_cstride, double* d_
     P.stream = d_stream2_.p;
     if (!items_s2_.empty()) {
       cudaEventRecord(ev0_, stream);
-      k_alm2leg_s2<S2_R, S2_NW><<<(unsigned)items_s2_.size(), (S2_NW + 1) * 32, 0, stream>>>(P);
+      k_alm2leg_s2<S2_R, S2_NW><<<(unsigned)items_s2_.size(), S2_NW * 32, 0, stream>>>(P);
       cudaEventRecord(ev1_, stream);
       ++launches_;
     }
@@ -1397,7 +1412,7 @@ void LegendreStage::leg2alm(const double* d_leg, double* d_alm, int64_t alm_cstr
     P.partoff = d_apartoff0_.p;
     if (!items_a0_.empty()) {
       cudaEventRecord(ev0_, stream);
-      k_leg2alm_s0<A0_R, A0_NW><<<(unsigned)items_a0_.size(), (A0_NW + 1) * 32, 0, stream>>>(P);
+      k_leg2alm_s0<A0_R, A0_NW><<<(unsigned)items_a0_.size(), A0_NW * 32, 0, stream>>>(P);
       cudaEventRecord(ev1_, stream);
       ++launches_;
     }
@@ -1424,7 +1439,7 @@ void LegendreStage::leg2alm(const double* d_leg, double* d_alm, int64_t alm_cstr
     P.partoff = d_apartoff2_.p;
     if (!items_a2_.empty()) {
       cudaEventRecord(ev0_, stream);
-      k_leg2alm_s2<A2_R, A2_NW><<<(unsigned)items_a2_.size(), (A2_NW + 1) * 32, 0, stream>>>(P);
+      k_leg2alm_s2<A2_R, A2_NW><<<(unsigned)items_a2_.size(), A2_NW * 32, 0, stream>>>(P);
       cudaEventRecord(ev1_, stream);
       ++launches_;
     }
