@@ -70,6 +70,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                             uint64_t* bar) {
@@ -168,29 +181,62 @@ struct LegParams {
 };
 
 // ------------------------------------------------------------------------------------------------
-// producer side of the coefficient pipeline.  Thread 0 of the CTA issues the 1-D TMA bulk copies of
-// chunk `cn` (counted over the whole CTA lifetime; the per-m stream is replayed once per tile in the
-// adjoint) into stage cn % NSTAGE, after every consumer warp released that stage.
+// producer side of the coefficient pipeline.  One thread issues the 1-D TMA bulk copies of chunk
+// `cn` (counted over the whole CTA lifetime; the per-m stream is replayed once per tile in the
+// adjoint) into stage cn % NSTAGE once every consumer warp released that stage.
+//   PROD == 1: a dedicated producer warp runs `pump` to completion (blocking on `empty`).
+//   PROD == 2: lane 0 of the last consumer warp calls `pump` at every chunk start and group
+//              boundary; it only blocks for the chunk it is about to consume itself and otherwise
+//              probes `empty` without waiting, so the consumer warps stay decoupled.
 // ------------------------------------------------------------------------------------------------
 template <bool WITH_STREAM>
-__device__ __forceinline__ void issue_chunk(int cn, int nchunks, const double* gcoef, const double* gstrm,
-                                            Coef (*s_coef)[LEG_CHUNK], Strm (*s_strm)[LEG_CHUNK],
-                                            uint64_t* full, uint64_t* empty) {
-  const int st = cn % NSTAGE;
-  const int c = cn % nchunks;
-  if (cn >= NSTAGE) mbar_wait(&empty[st], ((cn / NSTAGE) - 1) & 1);
-  const uint32_t bytes = LEG_CHUNK * sizeof(Coef) + (WITH_STREAM ? LEG_CHUNK * sizeof(Strm) : 0);
-  mbar_arrive_expect_tx(&full[st], bytes);
-  tma_load_1d(&s_coef[st][0], gcoef + (size_t)c * LEG_CHUNK * 2, LEG_CHUNK * sizeof(Coef), &full[st]);
-  if (WITH_STREAM)
-    tma_load_1d(&s_strm[st][0], gstrm + (size_t)c * LEG_CHUNK * 4, LEG_CHUNK * sizeof(Strm), &full[st]);
-}
+struct Pump {
+  int nissued, total, nchunks;
+  const double* gcoef;
+  const double* gstrm;
+  Coef (*s_coef)[LEG_CHUNK];
+  Strm (*s_strm)[LEG_CHUNK];
+  uint64_t* full;
+  uint64_t* empty;
+
+  __device__ __forceinline__ void issue(int cn) {
+    const int st = cn % NSTAGE;
+    const int c = cn % nchunks;
+    const uint32_t bytes = LEG_CHUNK * sizeof(Coef) + (WITH_STREAM ? LEG_CHUNK * sizeof(Strm) : 0);
+    mbar_arrive_expect_tx(&full[st], bytes);
+    tma_load_1d(&s_coef[st][0], gcoef + (size_t)c * LEG_CHUNK * 2, LEG_CHUNK * sizeof(Coef), &full[st]);
+    if (WITH_STREAM)
+      tma_load_1d(&s_strm[st][0], gstrm + (size_t)c * LEG_CHUNK * 4, LEG_CHUNK * sizeof(Strm), &full[st]);
+  }
+  // issue everything that can go out now, at most NSTAGE-1 chunks beyond `cg`; wait only for `cg`
+  __device__ __forceinline__ void run(int cg) {
+    while (nissued < total && nissued <= cg + NSTAGE - 1) {
+      if (nissued >= NSTAGE) {
+        const int st = nissued % NSTAGE;
+        const uint32_t par = ((nissued / NSTAGE) - 1) & 1;
+        if (nissued <= cg)
+          mbar_wait(&empty[st], par);
+        else if (!mbar_test(&empty[st], par))
+          break;
+      }
+      issue(nissued);
+      ++nissued;
+    }
+  }
+  // dedicated producer: everything, blocking
+  __device__ __forceinline__ void run_all() {
+    for (; nissued < total; ++nissued) {
+      if (nissued >= NSTAGE) mbar_wait(&empty[nissued % NSTAGE], ((nissued / NSTAGE) - 1) & 1);
+      issue(nissued);
+    }
+  }
+};
 
 // ================================================================================================
 // spin 0 synthesis:  leg_N/S = sum_n p_n A_n  +-  x sum_n p_n B_n
 // ================================================================================================
-template <int R, int NW>
-__global__ void __launch_bounds__(NW * 32) k_alm2leg_s0(LegParams P) {
+template <int R, int NW, int PROD>
+__global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ Strm s_strm[NSTAGE][LEG_CHUNK];
   __shared__ __align__(8) uint64_t s_full[NSTAGE];
@@ -215,9 +261,13 @@ __global__ void __launch_bounds__(NW * 32) k_alm2leg_s0(LegParams P) {
 
   const double* gcoef = P.coef + (size_t)P.off[mi] * 2;
   const double* gstrm = P.stream + (size_t)P.off[mi] * 4;
-  if (threadIdx.x == 0)
-    for (int cn = 0; cn < NSTAGE - 1 && cn < nchunks; ++cn)
-      issue_chunk<true>(cn, nchunks, gcoef, gstrm, s_coef, s_strm, s_full, s_empty);
+  Pump<true> pump{0, nchunks, nchunks, gcoef, gstrm, s_coef, s_strm, s_full, s_empty};
+  if (warp >= NW) {
+    if (PROD == 1 && warp == NW && lane == 0) pump.run_all();
+    return;
+  }
+  const bool issuer = (PROD == 2) && (threadIdx.x == (NW - 1) * 32);
+  if (issuer) pump.run(0);
 
   // ---------------- consumer warps ----------------
   double csq[R], lam1[R], lam2[R];
@@ -250,9 +300,10 @@ __global__ void __launch_bounds__(NW * 32) k_alm2leg_s0(LegParams P) {
 
   for (int c = 0; c < nchunks; ++c) {
     const int st = c % NSTAGE;
-    if (threadIdx.x == 0 && c + NSTAGE - 1 < nchunks)
-      issue_chunk<true>(c + NSTAGE - 1, nchunks, gcoef, gstrm, s_coef, s_strm, s_full, s_empty);
-    __syncwarp();
+    if (PROD == 2) {
+      if (issuer) pump.run(c);
+      __syncwarp();
+    }
     mbar_wait(&s_full[st], (c / NSTAGE) & 1);
     if (warp_act) {
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
@@ -307,6 +358,7 @@ __global__ void __launch_bounds__(NW * 32) k_alm2leg_s0(LegParams P) {
             }
           }
         }
+        if (PROD == 2 && issuer) pump.run(c);  // opportunistic refill, never blocks here
       }
     }
     __syncwarp();
@@ -336,8 +388,8 @@ __global__ void __launch_bounds__(NW * 32) k_alm2leg_s0(LegParams P) {
 //   P+N = sum alpha+ d+ ; P-N = sum alpha- d- ; P+S = sum (-1)^(l+m) alpha+ d- ; P-S = sum (-1)^(l+m) alpha- d+
 //   Q = P+ + P- ; U = -i (P+ - P-)
 // ================================================================================================
-template <int R, int NW>
-__global__ void __launch_bounds__(NW * 32) k_alm2leg_s2(LegParams P) {
+template <int R, int NW, int PROD>
+__global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ Strm s_strm[NSTAGE][LEG_CHUNK];
   __shared__ __align__(8) uint64_t s_full[NSTAGE];
@@ -362,9 +414,13 @@ __global__ void __launch_bounds__(NW * 32) k_alm2leg_s2(LegParams P) {
 
   const double* gcoef = P.coef + (size_t)P.off[mi] * 2;
   const double* gstrm = P.stream + (size_t)P.off[mi] * 4;
-  if (threadIdx.x == 0)
-    for (int cn = 0; cn < NSTAGE - 1 && cn < nchunks; ++cn)
-      issue_chunk<true>(cn, nchunks, gcoef, gstrm, s_coef, s_strm, s_full, s_empty);
+  Pump<true> pump{0, nchunks, nchunks, gcoef, gstrm, s_coef, s_strm, s_full, s_empty};
+  if (warp >= NW) {
+    if (PROD == 1 && warp == NW && lane == 0) pump.run_all();
+    return;
+  }
+  const bool issuer = (PROD == 2) && (threadIdx.x == (NW - 1) * 32);
+  if (issuer) pump.run(0);
 
   double x[R], lp1[R], lp2[R], lm1[R], lm2[R];
   double pnr[R], pni[R], mnr[R], mni[R];  // P+N, P-N
@@ -406,9 +462,10 @@ __global__ void __launch_bounds__(NW * 32) k_alm2leg_s2(LegParams P) {
 
   for (int c = 0; c < nchunks; ++c) {
     const int st = c % NSTAGE;
-    if (threadIdx.x == 0 && c + NSTAGE - 1 < nchunks)
-      issue_chunk<true>(c + NSTAGE - 1, nchunks, gcoef, gstrm, s_coef, s_strm, s_full, s_empty);
-    __syncwarp();
+    if (PROD == 2) {
+      if (issuer) pump.run(c);
+      __syncwarp();
+    }
     mbar_wait(&s_full[st], (c / NSTAGE) & 1);
     if (warp_act) {
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
@@ -488,6 +545,7 @@ __global__ void __launch_bounds__(NW * 32) k_alm2leg_s2(LegParams P) {
             }
           }
         }
+        if (PROD == 2 && issuer) pump.run(c);
       }
     }
     __syncwarp();
@@ -557,8 +615,8 @@ __device__ __forceinline__ void flush_chunk(const double (*s_red)[LEG_CHUNK * 4]
 // One work item = one m and a contiguous RANGE of pairs; the CTA walks the range tile by tile and
 // accumulates its own partial sums in global memory (read-modify-write by the same thread, L2
 // resident), so the number of partial buffers per m is the number of items, not of tiles.
-template <int R, int NW>
-__global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s0(LegParams P) {
+template <int R, int NW, int PROD>
+__global__ void __launch_bounds__((NW + (PROD == 1 ? 1 : 0)) * 32, 2) k_leg2alm_s0(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ double s_red[2][NW][LEG_CHUNK * 4];
   __shared__ __align__(8) uint64_t s_full[NSTAGE];
@@ -585,9 +643,13 @@ __global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s0(LegParams P) {
 
   const double* gcoef = P.coef + (size_t)P.off[mi] * 2;
   const int total_chunks = nchunks * ntile;
-  if (threadIdx.x == 0)
-    for (int cn = 0; cn < NSTAGE - 1 && cn < total_chunks; ++cn)
-      issue_chunk<false>(cn, nchunks, gcoef, nullptr, s_coef, nullptr, s_full, s_empty);
+  Pump<false> pump{0, total_chunks, nchunks, gcoef, nullptr, s_coef, nullptr, s_full, s_empty};
+  if (warp >= NW) {
+    if (PROD == 1 && warp == NW && lane == 0) pump.run_all();
+    return;
+  }
+  const bool issuer = (PROD == 2) && (threadIdx.x == (NW - 1) * 32);
+  if (issuer) pump.run(0);
 
   const double2* leg = reinterpret_cast<const double2*>(P.leg);
   const double k0 = P.k0[mi];
@@ -642,9 +704,10 @@ __global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s0(LegParams P) {
     for (int c = 0; c < nchunks; ++c, ++cg) {
       const int st = cg % NSTAGE;
       double* red = &s_red[cg & 1][warp][0];
-      if (threadIdx.x == 0 && cg + NSTAGE - 1 < total_chunks)
-        issue_chunk<false>(cg + NSTAGE - 1, nchunks, gcoef, nullptr, s_coef, nullptr, s_full, s_empty);
-      __syncwarp();
+      if (PROD == 2) {
+        if (issuer) pump.run(cg);
+        __syncwarp();
+      }
       mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
       for (int g = 0; g < LEG_CHUNK / LEG_GROUP; ++g) {
@@ -709,6 +772,7 @@ __global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s0(LegParams P) {
             }
           }
         }
+        if (PROD == 2 && issuer) pump.run(cg);
         if (!did) red[g * LEG_GROUP * 4 + lane] = 0.0;  // 8 steps x 4 values = 32 doubles
       }
       __syncwarp();
@@ -721,8 +785,8 @@ __global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s0(LegParams P) {
 
 // spin 2 adjoint:  G+_l = sum_pairs [ d+ w+N + (-1)^(l+m) d- w+S ],  G-_l = sum_pairs [ d- w-N + (-1)^(l+m) d+ w-S ]
 //   w+- = legQ +- i legU
-template <int R, int NW>
-__global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s2(LegParams P) {
+template <int R, int NW, int PROD>
+__global__ void __launch_bounds__((NW + (PROD == 1 ? 1 : 0)) * 32, 2) k_leg2alm_s2(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ double s_red[2][NW][LEG_CHUNK * 4];
   __shared__ __align__(8) uint64_t s_full[NSTAGE];
@@ -749,9 +813,13 @@ __global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s2(LegParams P) {
 
   const double* gcoef = P.coef + (size_t)P.off[mi] * 2;
   const int total_chunks = nchunks * ntile;
-  if (threadIdx.x == 0)
-    for (int cn = 0; cn < NSTAGE - 1 && cn < total_chunks; ++cn)
-      issue_chunk<false>(cn, nchunks, gcoef, nullptr, s_coef, nullptr, s_full, s_empty);
+  Pump<false> pump{0, total_chunks, nchunks, gcoef, nullptr, s_coef, nullptr, s_full, s_empty};
+  if (warp >= NW) {
+    if (PROD == 1 && warp == NW && lane == 0) pump.run_all();
+    return;
+  }
+  const bool issuer = (PROD == 2) && (threadIdx.x == (NW - 1) * 32);
+  if (issuer) pump.run(0);
 
   const double2* leg = reinterpret_cast<const double2*>(P.leg);
   const double kp = P.k0[mi], km = P.k1[mi];
@@ -840,9 +908,10 @@ __global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s2(LegParams P) {
     for (int c = 0; c < nchunks; ++c, ++cg) {
       const int st = cg % NSTAGE;
       double* red = &s_red[cg & 1][warp][0];
-      if (threadIdx.x == 0 && cg + NSTAGE - 1 < total_chunks)
-        issue_chunk<false>(cg + NSTAGE - 1, nchunks, gcoef, nullptr, s_coef, nullptr, s_full, s_empty);
-      __syncwarp();
+      if (PROD == 2) {
+        if (issuer) pump.run(cg);
+        __syncwarp();
+      }
       mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
       for (int g = 0; g < LEG_CHUNK / LEG_GROUP; ++g) {
@@ -933,12 +1002,452 @@ __global__ void __launch_bounds__(NW * 32, 2) k_leg2alm_s2(LegParams P) {
             }
           }
         }
+        if (PROD == 2 && issuer) pump.run(cg);
         if (!did) red[g * LEG_GROUP * 4 + lane] = 0.0;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
       named_bar_sync(1, NW * 32);
       flush_chunk<NW>(s_red[cg & 1], gpart + (size_t)c * LEG_CHUNK * 4, tidc, tile == 0);
+    }
+  }
+}
+
+// ================================================================================================
+// adjoint kernels, single-warp CTAs ("_w" variants)
+//
+// One CTA = one warp = one work item (one m, a contiguous range of ring pairs walked tile by tile,
+// tile = 32 R pairs).  No block-level barrier exists: a warp that is still ramping up, or that has
+// finished, never holds other warps' registers hostage, and the scheduler backfills with the next
+// item.  The 32-lane reduction of the 16 partial sums of every 4-step group goes through a padded
+// shared-memory transpose (16 STS.64 + 16 LDS.64 + 16 DADD + 1 shuffle) instead of a select-heavy
+// shuffle butterfly.  Reduced values are added into the item's partial-sum array in global memory
+// once per 64-step chunk (read-modify-write by the same lane; prefetched at chunk start).
+// The coefficient stream is staged by TMA bulk copies issued by lane 0; with a single consumer warp
+// a stage is free as soon as the warp has passed it, so only the `full` mbarriers are needed.
+// ================================================================================================
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// sum over the 32 lanes of v[k], k < 16, through shared memory; every lane returns the total of value
+// (lane & 15)
+__device__ __forceinline__ double warp_reduce16_smem(const double (&v)[16], double (*tr)[33], int lane) {
+  __syncwarp();  // readers of the previous round are done
+#pragma unroll
+  for (int k = 0; k < 16; ++k) tr[k][lane] = v[k];
+  __syncwarp();
+  const int j = lane & 15, h = (lane >> 4) * 16;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+  for (int t = 0; t < 16; t += 4) {
+    s0 += tr[j][h + t];
+    s1 += tr[j][h + t + 1];
+    s2 += tr[j][h + t + 2];
+    s3 += tr[j][h + t + 3];
+  }
+  double s = (s0 + s1) + (s2 + s3);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  return s;
+}
+
+struct WarpPipe {
+  Coef (*s_coef)[LEG_CHUNK];
+  uint64_t* full;
+  const double* gcoef;
+  int nchunks, total;
+  __device__ __forceinline__ void issue(int cn) const {
+    const int st = cn % NSTAGE;
+    mbar_arrive_expect_tx(&full[st], LEG_CHUNK * sizeof(Coef));
+    tma_load_1d(&s_coef[st][0], gcoef + (size_t)(cn % nchunks) * LEG_CHUNK * 2, LEG_CHUNK * sizeof(Coef),
+                &full[st]);
+  }
+};
+
+template <int R, int DBG = 0>
+__global__ void __launch_bounds__(32) k_leg2alm_s0_w(LegParams P) {
+  __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
+  __shared__ double s_tr[16][33];
+  __shared__ double s_res[LEG_CHUNK * 4];  // reduced sums of the current chunk
+  __shared__ __align__(8) uint64_t s_full[NSTAGE];
+  constexpr int TILE = R * 32;
+
+  const WorkItem it = P.items[blockIdx.x];
+  const int mi = it.mi;
+  const int m = (int)P.mval[mi];
+  const int nn = (int)P.nstep[mi];
+  const int nsteps = (nn + LEG_GROUP - 1) / LEG_GROUP * LEG_GROUP;
+  const int nchunks = (nsteps + LEG_CHUNK - 1) / LEG_CHUNK;
+  const int ntile = (it.np + TILE - 1) / TILE;
+  const int lane = threadIdx.x;
+
+  if (lane == 0) {
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(&s_full[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const WarpPipe pipe{s_coef, s_full, P.coef + (size_t)P.off[mi] * 2, nchunks, nchunks * ntile};
+  if (lane == 0)
+    for (int cn = 0; cn < NSTAGE - 1 && cn < pipe.total; ++cn) pipe.issue(cn);
+
+  const double2* leg = reinterpret_cast<const double2*>(P.leg);
+  const double k0 = P.k0[mi];
+  double* gpart = P.part + (size_t)P.partoff[blockIdx.x] * 4;
+  int cg = 0;
+
+  for (int tile = 0; tile < ntile; ++tile) {
+    const int tp0 = it.p0 + tile * TILE;
+    const int tnp = min(TILE, it.np - tile * TILE);
+    double csq[R], lam1[R], lam2[R];
+    double er[R], ei[R], orr[R], oi[R];
+    int sc[R];
+    bool act[R];
+    bool any_act = false;
+
+    auto load_in = [&](int r, int p) {
+      const int64_t rowoff = (int64_t)mi * P.mstr[p];
+      const double2 gN = leg[P.offN[p] + rowoff];
+      const int64_t oS = P.offS[p];
+      const double2 gS = oS >= 0 ? leg[oS + rowoff] : make_double2(0.0, 0.0);
+      const double cc = P.cth[p];
+      er[r] = gN.x + gS.x;
+      ei[r] = gN.y + gS.y;
+      orr[r] = cc * (gN.x - gS.x);
+      oi[r] = cc * (gN.y - gS.y);
+    };
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int pl = r * 32 + lane;
+      const bool valid = pl < tnp;
+      const int p = tp0 + (valid ? pl : 0);
+      act[r] = valid && (m <= P.mlim[p]);
+      any_act |= act[r];
+      const double c = P.cth[p];
+      csq[r] = c * c;
+      double mant;
+      int e;
+      pow_scaled(P.sth[p], m, mant, e);
+      to_scaled(k0 * mant, e, lam2[r], sc[r]);
+      if (!act[r]) {
+        lam2[r] = 0.0;
+        sc[r] = 0;
+      }
+      lam1[r] = 0.0;
+      er[r] = ei[r] = orr[r] = oi[r] = 0.0;
+      if (act[r] && sc[r] == 0) load_in(r, p);
+    }
+    const bool warp_act = __any_sync(0xffffffffu, any_act);
+
+    for (int c = 0; c < nchunks; ++c, ++cg) {
+      const int st = cg % NSTAGE;
+      if (lane == 0 && cg + NSTAGE - 1 < pipe.total) {
+        fence_proxy_async();  // the stage being refilled was read (generic proxy) during chunk cg-1
+        pipe.issue(cg + NSTAGE - 1);
+      }
+      // partial sums of the previous tiles for this chunk (element k*32 + lane), fetched early
+      double* gp = gpart + (size_t)c * LEG_CHUNK * 4 + lane;
+      double old[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) old[k] = (tile > 0) ? gp[k * 32] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_res[k * 32 + lane] = 0.0;  // groups that only ramp contribute 0
+      mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
+      const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
+      if (warp_act) {
+#pragma unroll 1
+        for (int g = 0; g < ng; ++g) {
+          {
+            bool mine0 = false, mineneg = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              mine0 |= act[r] && (sc[r] == 0);
+              mineneg |= (sc[r] < 0);
+            }
+            const bool any0 = __any_sync(0xffffffffu, mine0);
+            const Coef* cf = &s_coef[st][g * LEG_GROUP];
+            if (any0) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                double acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                  const Coef ab = cf[h * 4 + s];
+#pragma unroll
+                  for (int r = 0; r < R; ++r) {
+                    if (DBG != 2) {  // DBG == 2: timing experiment without the accumulation FMAs
+                      acc[4 * s + 0] = fma(lam2[r], er[r], acc[4 * s + 0]);
+                      acc[4 * s + 1] = fma(lam2[r], ei[r], acc[4 * s + 1]);
+                      acc[4 * s + 2] = fma(lam2[r], orr[r], acc[4 * s + 2]);
+                      acc[4 * s + 3] = fma(lam2[r], oi[r], acc[4 * s + 3]);
+                    } else if (r == 0) {
+                      acc[4 * s] += lam2[0];
+                    }
+                    const double t = fma(ab.a, csq[r], ab.b);
+                    const double nx = fma(t, lam2[r], lam1[r]);
+                    lam1[r] = lam2[r];
+                    lam2[r] = nx;
+                  }
+                }
+                double tot;
+                if (DBG == 1) {  // timing experiment: no cross-lane reduction
+                  tot = acc[lane & 15] + acc[(lane + 5) & 15];
+                } else {
+                  tot = warp_reduce16_smem(acc, s_tr, lane);
+                }
+                // 4-step group q = 2g + h: lower half-warp keeps even q, upper half odd q
+                if (lane < 16) s_res[(g * 2 + h) * 16 + lane] = tot;
+              }
+            } else {
+#pragma unroll
+              for (int s = 0; s < LEG_GROUP; ++s) {
+                const Coef ab = cf[s];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                  const double t = fma(ab.a, csq[r], ab.b);
+                  const double nx = fma(t, lam2[r], lam1[r]);
+                  lam1[r] = lam2[r];
+                  lam2[r] = nx;
+                }
+              }
+            }
+            if (__any_sync(0xffffffffu, mineneg)) {
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                if (sc[r] < 0 && is_big(lam2[r])) {
+                  lam1[r] *= SC_DOWN;
+                  lam2[r] *= SC_DOWN;
+                  sc[r] += 1;
+                  if (sc[r] == 0) load_in(r, tp0 + r * 32 + lane);
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gp[k * 32] = old[k] + s_res[k * 32 + lane];
+      __syncwarp();  // s_res is zeroed again at the top of the next chunk
+    }
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(32) k_leg2alm_s2_w(LegParams P) {
+  __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
+  __shared__ double s_tr[16][33];
+  __shared__ double s_res[LEG_CHUNK * 4];  // reduced sums of the current chunk
+  __shared__ __align__(8) uint64_t s_full[NSTAGE];
+  constexpr int TILE = R * 32;
+
+  const WorkItem it = P.items[blockIdx.x];
+  const int mi = it.mi;
+  const int m = (int)P.mval[mi];
+  const int nl = (int)P.nstep[mi];
+  const int nsteps = (nl + LEG_GROUP - 1) / LEG_GROUP * LEG_GROUP;
+  const int nchunks = (nsteps + LEG_CHUNK - 1) / LEG_CHUNK;
+  const int ntile = (it.np + TILE - 1) / TILE;
+  const int lane = threadIdx.x;
+
+  if (lane == 0) {
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(&s_full[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const WarpPipe pipe{s_coef, s_full, P.coef + (size_t)P.off[mi] * 2, nchunks, nchunks * ntile};
+  if (lane == 0)
+    for (int cn = 0; cn < NSTAGE - 1 && cn < pipe.total; ++cn) pipe.issue(cn);
+
+  const double2* leg = reinterpret_cast<const double2*>(P.leg);
+  const double kp = P.k0[mi], km = P.k1[mi];
+  const int pw = m >= 2 ? m - 2 : 2 - m;
+  const int q = m < 2 ? m : 2;
+  const int l0 = m > 2 ? m : 2;
+  const double sgnS = ((l0 + m) & 1) ? -1.0 : 1.0;
+  double* gpart = P.part + (size_t)P.partoff[blockIdx.x] * 4;
+  int cg = 0;
+
+  for (int tile = 0; tile < ntile; ++tile) {
+    const int tp0 = it.p0 + tile * TILE;
+    const int tnp = min(TILE, it.np - tile * TILE);
+    double x[R], lp1[R], lp2[R], lm1[R], lm2[R];
+    double wpNr[R], wpNi[R], wmSr[R], wmSi[R], wmNr[R], wmNi[R], wpSr[R], wpSi[R];
+    int scp[R], scm[R];
+    bool act[R];
+    bool any_act = false;
+
+    auto load_p = [&](int r, int p) {  // inputs multiplied by d+
+      const int64_t rowoff = (int64_t)mi * P.mstr[p];
+      const int64_t cs = P.cstr[p];
+      const double2 qN = leg[P.offN[p] + rowoff], uN = leg[P.offN[p] + rowoff + cs];
+      wpNr[r] = qN.x - uN.y;
+      wpNi[r] = qN.y + uN.x;
+      const int64_t oS = P.offS[p];
+      if (oS >= 0) {
+        const double2 qS = leg[oS + rowoff], uS = leg[oS + rowoff + cs];
+        wmSr[r] = sgnS * (qS.x + uS.y);
+        wmSi[r] = sgnS * (qS.y - uS.x);
+      } else {
+        wmSr[r] = wmSi[r] = 0.0;
+      }
+    };
+    auto load_m = [&](int r, int p) {  // inputs multiplied by d-
+      const int64_t rowoff = (int64_t)mi * P.mstr[p];
+      const int64_t cs = P.cstr[p];
+      const double2 qN = leg[P.offN[p] + rowoff], uN = leg[P.offN[p] + rowoff + cs];
+      wmNr[r] = qN.x + uN.y;
+      wmNi[r] = qN.y - uN.x;
+      const int64_t oS = P.offS[p];
+      if (oS >= 0) {
+        const double2 qS = leg[oS + rowoff], uS = leg[oS + rowoff + cs];
+        wpSr[r] = sgnS * (qS.x - uS.y);
+        wpSi[r] = sgnS * (qS.y + uS.x);
+      } else {
+        wpSr[r] = wpSi[r] = 0.0;
+      }
+    };
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int pl = r * 32 + lane;
+      const bool valid = pl < tnp;
+      const int p = tp0 + (valid ? pl : 0);
+      act[r] = valid && (m <= P.mlim[p]);
+      any_act |= act[r];
+      x[r] = P.cth[p];
+      double mant;
+      int e;
+      pow_scaled(P.sth[p], pw, mant, e);
+      double fs = 1.0, fc = 1.0;
+      const double s2 = P.sh[p] * P.sh[p], c2 = P.ch[p] * P.ch[p];
+      for (int k = 0; k < q; ++k) {
+        fs *= s2;
+        fc *= c2;
+      }
+      to_scaled(kp * mant * fs, e, lp2[r], scp[r]);
+      to_scaled(km * mant * fc, e, lm2[r], scm[r]);
+      if (!act[r]) {
+        lp2[r] = lm2[r] = 0.0;
+        scp[r] = scm[r] = 0;
+      }
+      lp1[r] = lm1[r] = 0.0;
+      wpNr[r] = wpNi[r] = wmSr[r] = wmSi[r] = 0.0;
+      wmNr[r] = wmNi[r] = wpSr[r] = wpSi[r] = 0.0;
+      if (act[r] && scp[r] == 0) load_p(r, p);
+      if (act[r] && scm[r] == 0) load_m(r, p);
+    }
+    const bool warp_act = __any_sync(0xffffffffu, any_act);
+
+    for (int c = 0; c < nchunks; ++c, ++cg) {
+      const int st = cg % NSTAGE;
+      if (lane == 0 && cg + NSTAGE - 1 < pipe.total) {
+        fence_proxy_async();
+        pipe.issue(cg + NSTAGE - 1);
+      }
+      double* gp = gpart + (size_t)c * LEG_CHUNK * 4 + lane;
+      double old[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) old[k] = (tile > 0) ? gp[k * 32] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_res[k * 32 + lane] = 0.0;  // groups that only ramp contribute 0
+      mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
+      const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
+      if (warp_act) {
+#pragma unroll 1
+        for (int g = 0; g < ng; ++g) {
+          {
+            bool mine0 = false, mineneg = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              mine0 |= act[r] && ((scp[r] == 0) || (scm[r] == 0));
+              mineneg |= (scp[r] < 0) || (scm[r] < 0);
+            }
+            const bool any0 = __any_sync(0xffffffffu, mine0);
+            const Coef* cf = &s_coef[st][g * LEG_GROUP];
+            if (any0) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                double acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                  const Coef ab = cf[h * 4 + s];
+#pragma unroll
+                  for (int r = 0; r < R; ++r) {
+                    acc[4 * s + 0] = fma(lp2[r], wpNr[r], acc[4 * s + 0]);
+                    acc[4 * s + 1] = fma(lp2[r], wpNi[r], acc[4 * s + 1]);
+                    acc[4 * s + 2] = fma(lm2[r], wmNr[r], acc[4 * s + 2]);
+                    acc[4 * s + 3] = fma(lm2[r], wmNi[r], acc[4 * s + 3]);
+                    if ((s & 1) == 0) {
+                      acc[4 * s + 0] = fma(lm2[r], wpSr[r], acc[4 * s + 0]);
+                      acc[4 * s + 1] = fma(lm2[r], wpSi[r], acc[4 * s + 1]);
+                      acc[4 * s + 2] = fma(lp2[r], wmSr[r], acc[4 * s + 2]);
+                      acc[4 * s + 3] = fma(lp2[r], wmSi[r], acc[4 * s + 3]);
+                    } else {
+                      acc[4 * s + 0] = fma(-lm2[r], wpSr[r], acc[4 * s + 0]);
+                      acc[4 * s + 1] = fma(-lm2[r], wpSi[r], acc[4 * s + 1]);
+                      acc[4 * s + 2] = fma(-lp2[r], wmSr[r], acc[4 * s + 2]);
+                      acc[4 * s + 3] = fma(-lp2[r], wmSi[r], acc[4 * s + 3]);
+                    }
+                    const double tp = fma(x[r], ab.a, ab.b);
+                    const double tm = fma(x[r], ab.a, -ab.b);
+                    const double np_ = fma(tp, lp2[r], -lp1[r]);
+                    const double nm_ = fma(tm, lm2[r], -lm1[r]);
+                    lp1[r] = lp2[r];
+                    lp2[r] = np_;
+                    lm1[r] = lm2[r];
+                    lm2[r] = nm_;
+                  }
+                }
+                const double tot = warp_reduce16_smem(acc, s_tr, lane);
+                if (lane < 16) s_res[(g * 2 + h) * 16 + lane] = tot;
+              }
+            } else {
+#pragma unroll
+              for (int s = 0; s < LEG_GROUP; ++s) {
+                const Coef ab = cf[s];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                  const double tp = fma(x[r], ab.a, ab.b);
+                  const double tm = fma(x[r], ab.a, -ab.b);
+                  const double np_ = fma(tp, lp2[r], -lp1[r]);
+                  const double nm_ = fma(tm, lm2[r], -lm1[r]);
+                  lp1[r] = lp2[r];
+                  lp2[r] = np_;
+                  lm1[r] = lm2[r];
+                  lm2[r] = nm_;
+                }
+              }
+            }
+            if (__any_sync(0xffffffffu, mineneg)) {
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const int p = tp0 + r * 32 + lane;
+                if (scp[r] < 0 && is_big(lp2[r])) {
+                  lp1[r] *= SC_DOWN;
+                  lp2[r] *= SC_DOWN;
+                  scp[r] += 1;
+                  if (scp[r] == 0) load_p(r, p);
+                }
+                if (scm[r] < 0 && is_big(lm2[r])) {
+                  lm1[r] *= SC_DOWN;
+                  lm2[r] *= SC_DOWN;
+                  scm[r] += 1;
+                  if (scm[r] == 0) load_m(r, p);
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gp[k * 32] = old[k] + s_res[k * 32 + lane];
+      __syncwarp();  // s_res is zeroed again at the top of the next chunk
     }
   }
 }
@@ -1123,10 +1632,59 @@ double LegendreStage::main_kernel_ms() const {
 
 namespace {
 // kernel configurations
-constexpr int S0_R = 4, S0_NW = 4;   // spin-0 synthesis: 512 pairs / tile
-constexpr int S2_R = 2, S2_NW = 4;   // spin-2 synthesis: 256 pairs / tile
-constexpr int A0_R = 8, A0_NW = 4;   // spin-0 adjoint:  1024 pairs / tile
-constexpr int A2_R = 4, A2_NW = 4;   // spin-2 adjoint:   512 pairs / tile
+// synthesis kernel variants (R pairs per thread, NW consumer warps); selectable at run time for tuning
+struct SynCfg { int R, NW; };
+static const SynCfg kSynCfgs[] = {{2, 4}, {4, 4}, {2, 8}, {3, 4}, {4, 2}, {4, 1}, {8, 1}, {2, 1}, {3, 1}, {2, 2}};
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+static int s0_cfg() { return env_int("HPSHT_S0_CFG", 1); }  // default <4,4>: 512 pairs / tile
+static int s2_cfg() { return env_int("HPSHT_S2_CFG", 0); }  // default <2,4>: 256 pairs / tile
+static int env_syn_prod() { return env_int("HPSHT_SYN_PROD", 1); }  // 1 dedicated producer warp, 2 polling
+static int env_adj_prod() { return env_int("HPSHT_ADJ_PROD", 2); }
+#define HP_LAUNCH_P(KERNEL, PROD, cfgidx, nitems, stream, P)                                          \
+  do {                                                                                                 \
+    const int xw = (PROD == 1) ? 32 : 0;                                                               \
+    switch (cfgidx) {                                                                                  \
+      case 0: KERNEL<2, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;            \
+      case 1: KERNEL<4, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;            \
+      case 2: KERNEL<2, 8, PROD><<<(unsigned)(nitems), 8 * 32 + xw, 0, stream>>>(P); break;            \
+      case 3: KERNEL<3, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;            \
+      case 4: KERNEL<4, 2, PROD><<<(unsigned)(nitems), 2 * 32 + xw, 0, stream>>>(P); break;            \
+      case 5: KERNEL<4, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
+      case 6: KERNEL<8, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
+      case 7: KERNEL<2, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
+      case 8: KERNEL<3, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
+      default: KERNEL<2, 2, PROD><<<(unsigned)(nitems), 2 * 32 + xw, 0, stream>>>(P); break;           \
+    }                                                                                                  \
+  } while (0)
+#define HP_LAUNCH(KERNEL, prod, cfgidx, nitems, stream, P)                                            \
+  do {                                                                                                 \
+    if ((prod) == 1) HP_LAUNCH_P(KERNEL, 1, cfgidx, nitems, stream, P);                                \
+    else HP_LAUNCH_P(KERNEL, 2, cfgidx, nitems, stream, P);                                            \
+  } while (0)
+static int a0_cfg() { return env_int("HPSHT_A0_CFG", 1); }  // block-mode adjoint <4,4>
+static int a2_cfg() { return env_int("HPSHT_A2_CFG", 0); }  // block-mode adjoint <2,4>
+// adjoint kernel family: 1 = single-warp CTAs (k_leg2alm_*_w), 0 = 4-warp CTAs with a chunk barrier
+static int adj_warp_mode() { return env_int("HPSHT_ADJ_WARP", 1); }
+static int a0w_R() { return env_int("HPSHT_A0W_R", 6); }
+static int a2w_R() { return env_int("HPSHT_A2W_R", 3); }
+#define HP_LAUNCH_W(KERNEL, Rval, nitems, stream, P)                                                  \
+  do {                                                                                                 \
+    switch (Rval) {                                                                                    \
+      case 2: KERNEL<2><<<(unsigned)(nitems), 32, 0, stream>>>(P); break;                              \
+      case 3: KERNEL<3><<<(unsigned)(nitems), 32, 0, stream>>>(P); break;                              \
+      case 4: KERNEL<4><<<(unsigned)(nitems), 32, 0, stream>>>(P); break;                              \
+      case 6: KERNEL<6><<<(unsigned)(nitems), 32, 0, stream>>>(P); break;                              \
+      default: KERNEL<8><<<(unsigned)(nitems), 32, 0, stream>>>(P); break;                             \
+    }                                                                                                  \
+  } while (0)
+static int adj_tile(int spin) {
+  if (adj_warp_mode()) return 32 * (spin == 0 ? a0w_R() : a2w_R());
+  const SynCfg c = kSynCfgs[spin == 0 ? a0_cfg() : a2_cfg()];
+  return c.R * c.NW * 32;
+}
 
 // Work list: for every local m (ascending == descending cost; CTAs are handed out in blockIdx
 // order) the active tiles, i.e. those holding at least one pair with mlim >= m.  Pairs are sorted
@@ -1252,7 +1810,8 @@ void LegendreStage::ensure_spin(int spin, cudaStream_t stream) {
   build_legendre_tables(lmax_, mval_.data(), nm_, LEG_CHUNK, spin == 0, spin != 0, T);
   size_t part_steps = 0;
   // enough adjoint items to fill the GPU several times over even when a rank owns few m's
-  const int adj_groups = (int)std::max<int64_t>(1, (4096 + nm_ - 1) / std::max<int64_t>(nm_, 1));
+  const int64_t want_items = adj_warp_mode() ? 8192 : 4096;
+  const int adj_groups = (int)std::max<int64_t>(1, (want_items + nm_ - 1) / std::max<int64_t>(nm_, 1));
   if (spin == 0) {
     d_nstep0_.upload(T.nstep0.data(), T.nstep0.size(), stream);
     d_off0_.upload(T.off0.data(), T.off0.size(), stream);
@@ -1261,8 +1820,8 @@ void LegendreStage::ensure_spin(int spin, cudaStream_t stream) {
     d_k0_.upload(T.k0.data(), T.k0.size(), stream);
     d_stream0_.alloc((size_t)T.off0[(size_t)nm_] * 4);
     d_stream0_.zero(stream);
-    make_items(pairs_, mval_, T.nstep0, false, S0_R * S0_NW * 32, 0, items_s0_, nullptr, nullptr);
-    make_items(pairs_, mval_, T.nstep0, false, A0_R * A0_NW * 32, adj_groups, items_a0_, &afirst0_, &acount0_);
+    make_items(pairs_, mval_, T.nstep0, false, kSynCfgs[s0_cfg()].R * kSynCfgs[s0_cfg()].NW * 32, 0, items_s0_, nullptr, nullptr);
+    make_items(pairs_, mval_, T.nstep0, false, adj_tile(0), adj_groups, items_a0_, &afirst0_, &acount0_);
     apartoff0_.resize(items_a0_.size());
     for (size_t i = 0; i < items_a0_.size(); ++i) {
       apartoff0_[i] = (int64_t)part_steps;
@@ -1285,8 +1844,8 @@ void LegendreStage::ensure_spin(int spin, cudaStream_t stream) {
     d_km2_.upload(T.km2.data(), T.km2.size(), stream);
     d_stream2_.alloc((size_t)T.off2[(size_t)nm_] * 4);
     d_stream2_.zero(stream);
-    make_items(pairs_, mval_, T.nstep2, true, S2_R * S2_NW * 32, 0, items_s2_, nullptr, nullptr);
-    make_items(pairs_, mval_, T.nstep2, true, A2_R * A2_NW * 32, adj_groups, items_a2_, &afirst2_, &acount2_);
+    make_items(pairs_, mval_, T.nstep2, true, kSynCfgs[s2_cfg()].R * kSynCfgs[s2_cfg()].NW * 32, 0, items_s2_, nullptr, nullptr);
+    make_items(pairs_, mval_, T.nstep2, true, adj_tile(2), adj_groups, items_a2_, &afirst2_, &acount2_);
     apartoff2_.resize(items_a2_.size());
     for (size_t i = 0; i < items_a2_.size(); ++i) {
       apartoff2_[i] = (int64_t)part_steps;
@@ -1350,7 +1909,7 @@ void LegendreStage::alm2leg(const double* d_alm, int64_t alm_cstride, double* d_
     P.stream = d_stream0_.p;
     if (!items_s0_.empty()) {
       cudaEventRecord(ev0_, stream);
-      k_alm2leg_s0<S0_R, S0_NW><<<(unsigned)items_s0_.size(), S0_NW * 32, 0, stream>>>(P);
+      HP_LAUNCH(k_alm2leg_s0, env_syn_prod(), s0_cfg(), items_s0_.size(), stream, P);
       cudaEventRecord(ev1_, stream);
       ++launches_;
     }
@@ -1374,7 +1933,7 @@ void LegendreStage::alm2leg(const double* d_alm, int64_t alm_cstride, double* d_
     P.stream = d_stream2_.p;
     if (!items_s2_.empty()) {
       cudaEventRecord(ev0_, stream);
-      k_alm2leg_s2<S2_R, S2_NW><<<(unsigned)items_s2_.size(), S2_NW * 32, 0, stream>>>(P);
+      HP_LAUNCH(k_alm2leg_s2, env_syn_prod(), s2_cfg(), items_s2_.size(), stream, P);
       cudaEventRecord(ev1_, stream);
       ++launches_;
     }
@@ -1412,7 +1971,17 @@ void LegendreStage::leg2alm(const double* d_leg, double* d_alm, int64_t alm_cstr
     P.partoff = d_apartoff0_.p;
     if (!items_a0_.empty()) {
       cudaEventRecord(ev0_, stream);
-      k_leg2alm_s0<A0_R, A0_NW><<<(unsigned)items_a0_.size(), A0_NW * 32, 0, stream>>>(P);
+      if (adj_warp_mode())
+        if (env_int("HPSHT_DBG", 0) == 1) {
+          if (a0w_R() == 4) k_leg2alm_s0_w<4, 1><<<(unsigned)items_a0_.size(), 32, 0, stream>>>(P);
+          else k_leg2alm_s0_w<8, 1><<<(unsigned)items_a0_.size(), 32, 0, stream>>>(P);
+        } else if (env_int("HPSHT_DBG", 0) == 2) {
+          if (a0w_R() == 4) k_leg2alm_s0_w<4, 2><<<(unsigned)items_a0_.size(), 32, 0, stream>>>(P);
+          else k_leg2alm_s0_w<8, 2><<<(unsigned)items_a0_.size(), 32, 0, stream>>>(P);
+        } else
+          HP_LAUNCH_W(k_leg2alm_s0_w, a0w_R(), items_a0_.size(), stream, P);
+      else
+        HP_LAUNCH(k_leg2alm_s0, env_adj_prod(), a0_cfg(), items_a0_.size(), stream, P);
       cudaEventRecord(ev1_, stream);
       ++launches_;
     }
@@ -1439,7 +2008,10 @@ void LegendreStage::leg2alm(const double* d_leg, double* d_alm, int64_t alm_cstr
     P.partoff = d_apartoff2_.p;
     if (!items_a2_.empty()) {
       cudaEventRecord(ev0_, stream);
-      k_leg2alm_s2<A2_R, A2_NW><<<(unsigned)items_a2_.size(), A2_NW * 32, 0, stream>>>(P);
+      if (adj_warp_mode())
+        HP_LAUNCH_W(k_leg2alm_s2_w, a2w_R(), items_a2_.size(), stream, P);
+      else
+        HP_LAUNCH(k_leg2alm_s2, env_adj_prod(), a2_cfg(), items_a2_.size(), stream, P);
       cudaEventRecord(ev1_, stream);
       ++launches_;
     }

@@ -39,11 +39,19 @@ template <bool INV>
 __device__ __forceinline__ double2 mul_pm_i(double2 a) {
   return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
 }
-template <bool INV>
-__device__ __forceinline__ double2 twiddle(const double2* __restrict__ tw, int idx) {
-  const double2 t = __ldg(&tw[idx]);
-  return INV ? make_double2(t.x, -t.y) : t;
-}
+// T-th roots of unity exp(-2 pi i k / T) (T a power of two), two-level shared-memory table:
+// value(k) = hi[k >> 6] * lo[k & 63]; the inverse transform conjugates.
+struct Tw {
+  const double2* hi;
+  const double2* lo;
+  int T;
+  template <bool INV>
+  __device__ __forceinline__ double2 get(int k) const {
+    const double2 a = hi[k >> 6], b = lo[k & 63];
+    const double2 t = make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+    return INV ? make_double2(t.x, -t.y) : t;
+  }
+};
 
 // exp(i m phi0) with the rounding error of the product m*phi0 compensated
 __device__ __forceinline__ double2 phase(int m, double phi0) {
@@ -61,7 +69,8 @@ struct Roots {
   const double2* lo;
   __device__ __forceinline__ double2 operator()(int q) const { return cmul(hi[q >> 6], lo[q & 63]); }
 };
-__device__ __forceinline__ void build_roots(double2* hi, double2* lo, int n, int tid, int nt) {
+// sign = +1: exp(+2 pi i q / n) ; sign = -1: exp(-2 pi i q / n)
+__device__ __forceinline__ void build_roots(double2* hi, double2* lo, int n, double sign, int tid, int nt) {
   const int nhi = (n >> 6) + 1;
   const double inv = 1.0 / (double)n;
   for (int i = tid; i < nhi + 64; i += nt) {
@@ -70,9 +79,9 @@ __device__ __forceinline__ void build_roots(double2* hi, double2* lo, int n, int
     double s, c;
     sincospi(2.0 * (double)q * inv, &s, &c);
     if (is_lo)
-      lo[i - nhi] = make_double2(c, s);
+      lo[i - nhi] = make_double2(c, sign * s);
     else
-      hi[i] = make_double2(c, s);
+      hi[i] = make_double2(c, sign * s);
   }
 }
 
@@ -80,20 +89,20 @@ __device__ __forceinline__ void build_roots(double2* hi, double2* lo, int n, int
 // in-place power-of-two FFT passes over shared memory (all threads of the CTA participate)
 //   DIF: natural order in, bit-reversed out.  DIT: bit-reversed in, natural out.
 //   INV = false: exp(-2 pi i jk/M);  INV = true: exp(+2 pi i jk/M).  Unnormalised.
-//   tw[k] = exp(-2 pi i k / twn), k < twn/2, twn >= M.
+//   tw: two-level shared-memory table of the T-th roots exp(-2 pi i k / T), T >= M.
 // ------------------------------------------------------------------------------------------------
 template <bool INV>
-__device__ void fft_dif(double2* buf, int M, const double2* __restrict__ tw, int twn, int tid, int nt) {
+__device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt) {
   if (M < 2) return;
   const int lg = 31 - __clz(M);
   int L = M;
   if (lg & 1) {
     const int h = L >> 1;
-    const int ts = twn / L;
+    const int ts = tw.T / L;
     for (int i = tid; i < h; i += nt) {
       const double2 a = buf[i], b = buf[i + h];
       buf[i] = cadd(a, b);
-      buf[i + h] = cmul(csub(a, b), twiddle<INV>(tw, i * ts));
+      buf[i + h] = cmul(csub(a, b), tw.get<INV>(i * ts));
     }
     L >>= 1;
     __syncthreads();
@@ -101,13 +110,13 @@ __device__ void fft_dif(double2* buf, int M, const double2* __restrict__ tw, int
   while (L >= 4) {
     const int q = L >> 2;
     const int lq = 31 - __clz(q);
-    const int ts = twn / L;
+    const int ts = tw.T / L;
     for (int i = tid; i < (M >> 2); i += nt) {
       const int j = i & (q - 1);
       const int b = ((i >> lq) * L) + j;
       const double2 x0 = buf[b], x1 = buf[b + q], x2 = buf[b + 2 * q], x3 = buf[b + 3 * q];
-      const double2 w1 = twiddle<INV>(tw, j * ts);
-      const double2 w2 = twiddle<INV>(tw, 2 * j * ts);
+      const double2 w1 = tw.get<INV>(j * ts);
+      const double2 w2 = make_double2(fma(w1.x, w1.x, -w1.y * w1.y), 2.0 * w1.x * w1.y);  // w1^2
       const double2 a0 = cadd(x0, x2), a2 = cmul(csub(x0, x2), w1);
       const double2 a1 = cadd(x1, x3), a3 = mul_pm_i<INV>(cmul(csub(x1, x3), w1));
       buf[b] = cadd(a0, a1);
@@ -121,7 +130,7 @@ __device__ void fft_dif(double2* buf, int M, const double2* __restrict__ tw, int
 }
 
 template <bool INV>
-__device__ void fft_dit(double2* buf, int M, const double2* __restrict__ tw, int twn, int tid, int nt) {
+__device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt) {
   if (M < 2) return;
   const int lg = 31 - __clz(M);
   int L = 1;
@@ -138,13 +147,13 @@ __device__ void fft_dit(double2* buf, int M, const double2* __restrict__ tw, int
     L <<= 2;
     const int q = L >> 2;
     const int lq = 31 - __clz(q);
-    const int ts = twn / L;
+    const int ts = tw.T / L;
     for (int i = tid; i < (M >> 2); i += nt) {
       const int j = i & (q - 1);
       const int b = ((i >> lq) * L) + j;
       const double2 x0 = buf[b], x1 = buf[b + q], x2 = buf[b + 2 * q], x3 = buf[b + 3 * q];
-      const double2 w1 = twiddle<INV>(tw, j * ts);
-      const double2 w2 = twiddle<INV>(tw, 2 * j * ts);
+      const double2 w1 = tw.get<INV>(j * ts);
+      const double2 w2 = make_double2(fma(w1.x, w1.x, -w1.y * w1.y), 2.0 * w1.x * w1.y);  // w1^2
       const double2 t1 = cmul(x1, w2), t3 = cmul(x3, w2);
       const double2 a0 = cadd(x0, t1), a1 = csub(x0, t1);
       const double2 a2 = cadd(x2, t3), a3 = csub(x2, t3);
@@ -177,9 +186,9 @@ __device__ void bitrev_permute(double2* buf, int M, int tid, int nt) {
 //   otherwise Bluestein: src may be A itself or another buffer; the result lands in A[0..r) and
 //   A[r..M) is clobbered.  Caller synchronised before; result visible to all threads on return.
 __device__ void idft_r(double2* A, const double2* src, int r, int M, const double2* __restrict__ hhat,
-                       const Roots& W, const double2* __restrict__ tw, int twn, int tid, int nt) {
+                       const Roots& W, const Tw& tw, int tid, int nt) {
   if (M == 0) {  // r is a power of two
-    fft_dif<true>(A, r, tw, twn, tid, nt);
+    fft_dif<true>(A, r, tw, tid, nt);
     bitrev_permute(A, r, tid, nt);
     return;
   }
@@ -188,18 +197,18 @@ __device__ void idft_r(double2* A, const double2* src, int r, int M, const doubl
   for (int k = tid; k < M; k += nt) {
     double2 v = make_double2(0.0, 0.0);
     if (k < r) {
-      const int q = (int)(((long long)k * k) % two_r);
+      const int q = (int)(((unsigned)k * (unsigned)k) % (unsigned)two_r);
       v = cmul(src[k], W(2 * q));
     }
     A[k] = v;
   }
   __syncthreads();
-  fft_dif<false>(A, M, tw, twn, tid, nt);
+  fft_dif<false>(A, M, tw, tid, nt);
   for (int k = tid; k < M; k += nt) A[k] = cmul(A[k], __ldg(&hhat[k]));
   __syncthreads();
-  fft_dit<true>(A, M, tw, twn, tid, nt);
+  fft_dit<true>(A, M, tw, tid, nt);
   for (int k = tid; k < r; k += nt) {
-    const int q = (int)(((long long)k * k) % two_r);
+    const int q = (int)(((unsigned)k * (unsigned)k) % (unsigned)two_r);
     A[k] = cmul(A[k], W(2 * q));
   }
   __syncthreads();
@@ -211,10 +220,13 @@ __device__ void idft_r(double2* A, const double2* src, int r, int M, const doubl
 struct SmemLayout {
   double2* A;
   double2* B;
-  double2* hi;    // rmax*4/64 + 2
+  double2* hi;    // rmax*4/64 + 2   n-th roots (n = 4r)
   double2* lo;    // 64
+  double2* hi2;   // Tmax/64 + 2     T-th roots of the power-of-two FFT (T = M or r)
+  double2* lo2;   // 64
   double2* part;  // nthreads (fold scratch)
 };
+__host__ __device__ __forceinline__ int size_T(int rmax, int Mmax) { return Mmax > rmax ? Mmax : rmax; }
 __host__ __device__ __forceinline__ int size_A(int rmax, int Mmax) {
   return Mmax > 2 * rmax + 2 ? Mmax : 2 * rmax + 2;
 }
@@ -229,19 +241,24 @@ __device__ __forceinline__ SmemLayout carve(unsigned char* base, int rmax, int M
   p += (rmax * 4) / 64 + 2;
   s.lo = p;
   p += 64;
+  s.hi2 = p;
+  p += size_T(rmax, Mmax) / 64 + 2;
+  s.lo2 = p;
+  p += 64;
   s.part = p;
   return s;
 }
 size_t smem_bytes(int rmax, int Mmax, int nt) {
-  return sizeof(double2) * ((size_t)size_A(rmax, Mmax) + (Mmax > 0 ? rmax : 0) + (rmax * 4) / 64 + 2 + 64 + nt);
+  return sizeof(double2) * ((size_t)size_A(rmax, Mmax) + (Mmax > 0 ? rmax : 0) + (rmax * 4) / 64 + 2 + 64 +
+                           size_T(rmax, Mmax) / 64 + 2 + 64 + nt);
 }
 
 // ------------------------------------------------------------------------------------------------
 // leg2map
 // ------------------------------------------------------------------------------------------------
-__global__ void k_leg2map(const RingDesc* __restrict__ desc, int first, const double2* __restrict__ leg,
+__global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ desc, int first, const double2* __restrict__ leg,
                           double* __restrict__ map, int64_t map_cstride, int64_t nm, int64_t nring,
-                          const double2* __restrict__ tw, int twn, const double2* __restrict__ hhat_all,
+                          const double2* __restrict__ hhat_all,
                           int rmax, int Mmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -252,8 +269,10 @@ __global__ void k_leg2map(const RingDesc* __restrict__ desc, int first, const do
   const int mmax = (int)nm - 1;
   const double2* row = leg + ((int64_t)comp * nring + d.ir) * nm;
   const Roots W{S.hi, S.lo};
+  const Tw TW{S.hi2, S.lo2, d.M ? d.M : d.r};
 
-  build_roots(S.hi, S.lo, n, tid, nt);
+  build_roots(S.hi, S.lo, n, 1.0, tid, nt);
+  build_roots(S.hi2, S.lo2, d.M ? d.M : d.r, -1.0, tid, nt);
 
   // ---- phase shift + alias fold: X[k], k = 0..N ----
   {
@@ -330,8 +349,8 @@ __global__ void k_leg2map(const RingDesc* __restrict__ desc, int first, const do
   const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (d.M == 0) {
     // power-of-two r: both halves transformed in place, one fully coalesced store
-    idft_r(S.A, S.A, r, 0, nullptr, W, tw, twn, tid, nt);
-    idft_r(S.A + r, S.A + r, r, 0, nullptr, W, tw, twn, tid, nt);
+    idft_r(S.A, S.A, r, 0, nullptr, W, TW, tid, nt);
+    idft_r(S.A + r, S.A + r, r, 0, nullptr, W, TW, tid, nt);
     // ---- pixels: x[4j..4j+3] = Re U[j], Im U[j], Re V[j], Im V[j] ----
     if (al16) {
       double2* out2 = reinterpret_cast<double2*>(out);
@@ -349,7 +368,7 @@ __global__ void k_leg2map(const RingDesc* __restrict__ desc, int first, const do
     for (int k = tid; k < r; k += nt) S.B[k] = S.A[k + r];
     __syncthreads();
     for (int half = 0; half < 2; ++half) {
-      idft_r(S.A, half == 0 ? S.A : S.B, r, d.M, hhat, W, tw, twn, tid, nt);
+      idft_r(S.A, half == 0 ? S.A : S.B, r, d.M, hhat, W, TW, tid, nt);
       if (al16) {
         double2* out2 = reinterpret_cast<double2*>(out);
         for (int j = tid; j < r; j += nt) out2[2 * j + half] = S.A[j];
@@ -367,9 +386,9 @@ __global__ void k_leg2map(const RingDesc* __restrict__ desc, int first, const do
 // ------------------------------------------------------------------------------------------------
 // map2leg
 // ------------------------------------------------------------------------------------------------
-__global__ void k_map2leg(const RingDesc* __restrict__ desc, int first, const double* __restrict__ map,
+__global__ void __launch_bounds__(1024) k_map2leg(const RingDesc* __restrict__ desc, int first, const double* __restrict__ map,
                           int64_t map_cstride, double2* __restrict__ leg, int64_t nm, int64_t nring,
-                          const double2* __restrict__ tw, int twn, const double2* __restrict__ hhat_all,
+                          const double2* __restrict__ hhat_all,
                           int rmax, int Mmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -380,8 +399,10 @@ __global__ void k_map2leg(const RingDesc* __restrict__ desc, int first, const do
   const int mmax = (int)nm - 1;
   double2* row = leg + ((int64_t)comp * nring + d.ir) * nm;
   const Roots W{S.hi, S.lo};
+  const Tw TW{S.hi2, S.lo2, d.M ? d.M : d.r};
 
-  build_roots(S.hi, S.lo, n, tid, nt);
+  build_roots(S.hi, S.lo, n, 1.0, tid, nt);
+  build_roots(S.hi2, S.lo2, d.M ? d.M : d.r, -1.0, tid, nt);
 
   // ---- pixels -> conj(u) | conj(v) ;  u[j] = x[4j] + i x[4j+1], v[j] = x[4j+2] + i x[4j+3] ----
   const double* in = map + (int64_t)comp * map_cstride + d.pixoff;
@@ -401,17 +422,17 @@ __global__ void k_map2leg(const RingDesc* __restrict__ desc, int first, const do
 
   const double2* hhat = d.hoff >= 0 ? hhat_all + d.hoff : nullptr;
   if (d.M == 0) {
-    idft_r(S.A, S.A, r, 0, nullptr, W, tw, twn, tid, nt);          // = conj(Uhat)
-    idft_r(S.A + r, S.A + r, r, 0, nullptr, W, tw, twn, tid, nt);  // = conj(Vhat)
+    idft_r(S.A, S.A, r, 0, nullptr, W, TW, tid, nt);          // = conj(Uhat)
+    idft_r(S.A + r, S.A + r, r, 0, nullptr, W, TW, tid, nt);  // = conj(Vhat)
   } else {
-    idft_r(S.A, S.A, r, d.M, hhat, W, tw, twn, tid, nt);  // conj(Uhat) in A[0..r)
+    idft_r(S.A, S.A, r, d.M, hhat, W, TW, tid, nt);  // conj(Uhat) in A[0..r)
     for (int k = tid; k < r; k += nt) {                   // swap: conj(Uhat) -> B, conj(v) -> A
       const double2 t = S.A[k];
       S.A[k] = S.B[k];
       S.B[k] = t;
     }
     __syncthreads();
-    idft_r(S.A, S.A, r, d.M, hhat, W, tw, twn, tid, nt);  // conj(Vhat) in A[0..r)
+    idft_r(S.A, S.A, r, d.M, hhat, W, TW, tid, nt);  // conj(Vhat) in A[0..r)
     for (int k = tid; k < r; k += nt) {                   // A[0..r) = conj(Uhat), A[r..2r) = conj(Vhat)
       const double2 vh = S.A[k];
       S.A[k] = S.B[k];
@@ -457,14 +478,16 @@ __global__ void k_map2leg(const RingDesc* __restrict__ desc, int first, const do
 // chirp spectrum of one r:  hhat = DIF_forward(h) / M,  h[d] = conj(c[|d|]) circularly, |d| < r
 __global__ void k_build_hhat(const int* __restrict__ rs, const int* __restrict__ Ms,
                              const int64_t* __restrict__ hoffs, double2* __restrict__ hhat_all,
-                             const double2* __restrict__ tw, int twn, int rmax, int Mmax) {
+                             int rmax, int Mmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const SmemLayout S = carve(smem_raw, rmax, Mmax, nt);
   const int r = rs[blockIdx.x], M = Ms[blockIdx.x];
   const int n = 4 * r;
   const Roots W{S.hi, S.lo};
-  build_roots(S.hi, S.lo, n, tid, nt);
+  const Tw TW{S.hi2, S.lo2, M};
+  build_roots(S.hi, S.lo, n, 1.0, tid, nt);
+  build_roots(S.hi2, S.lo2, M, -1.0, tid, nt);
   __syncthreads();
   const double inv = 1.0 / (double)M;
   for (int k = tid; k < M; k += nt) {
@@ -482,7 +505,7 @@ __global__ void k_build_hhat(const int* __restrict__ rs, const int* __restrict__
     S.A[k] = v;
   }
   __syncthreads();
-  fft_dif<false>(S.A, M, tw, twn, tid, nt);
+  fft_dif<false>(S.A, M, TW, tid, nt);
   double2* out = hhat_all + hoffs[blockIdx.x];
   for (int k = tid; k < M; k += nt) out[k] = S.A[k];
 }
@@ -507,7 +530,6 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
   std::vector<int> rs, Ms;
   std::vector<int64_t> hoffs;
   int64_t htotal = 0;
-  int twn = 2;
   for (int64_t i = 0; i < nring; ++i) {
     const int64_t n = nphi[i];
     HP_REQUIRE(n >= 4 && n % 4 == 0, HPSHT_ERR_UNSUPPORTED,
@@ -525,10 +547,8 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     if (pow2) {
       d.M = 0;
       d.hoff = -1;
-      twn = std::max(twn, d.r);
     } else {
       d.M = next_pow2(2 * d.r - 1);
-      twn = std::max(twn, d.M);
       auto it = hoff_of_r.find(d.r);
       if (it == hoff_of_r.end()) {
         hoff_of_r[d.r] = htotal;
@@ -542,18 +562,6 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
       }
     }
     desc_.push_back(d);
-  }
-  twn_ = twn;
-  // twiddle table exp(-2 pi i k / twn), k < twn/2, in long double on the host
-  {
-    std::vector<double> tw((size_t)std::max(1, twn / 2) * 2);
-    const long double PI = 3.14159265358979323846264338327950288419716939937510L;
-    for (int k = 0; k < std::max(1, twn / 2); ++k) {
-      const long double a = -2.0L * PI * (long double)k / (long double)twn;
-      tw[2 * (size_t)k] = (double)cosl(a);
-      tw[2 * (size_t)k + 1] = (double)sinl(a);
-    }
-    d_tw_.upload(tw.data(), tw.size(), stream);
   }
   // size classes: big CTAs for big rings; Bluestein rings need the extra work buffer
   std::stable_sort(desc_.begin(), desc_.end(), [](const RingDesc& a, const RingDesc& b) {
@@ -579,7 +587,9 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     }
     c.count = (int)(j - i);
     const int work = std::max(c.Mmax, c.rmax);
-    c.threads = work > 2048 ? 512 : (work > 512 ? 256 : (work > 64 ? 128 : 64));
+    const char* ev = getenv("HPSHT_FFT_THREADS_BIG");
+    const int big = ev ? atoi(ev) : 1024;
+    c.threads = work > 2048 ? big : (work > 512 ? 256 : (work > 64 ? 128 : 64));
     c.smem = smem_bytes(c.rmax, c.Mmax, c.threads);
     classes_.push_back(c);
     i = j;
@@ -608,7 +618,7 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     HP_CUDA(cudaFuncSetAttribute(k_build_hhat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_build_hhat<<<(unsigned)rs.size(), nt, sm, stream>>>(
         d_rs.p, d_Ms.p, d_hoffs.p, reinterpret_cast<double2*>(d_hhat_.p),
-        reinterpret_cast<const double2*>(d_tw_.p), twn_, rmax, Mmax);
+        rmax, Mmax);
     HP_CUDA(cudaGetLastError());
     HP_CUDA(cudaStreamSynchronize(stream));
   }
@@ -621,7 +631,7 @@ void RingFFT::leg2map(const double* d_leg, double* d_map, int64_t map_cstride, i
     dim3 grid((unsigned)c.count, (unsigned)ncomp);
     k_leg2map<<<grid, c.threads, c.smem, stream>>>(
         d_desc_.p, c.first, reinterpret_cast<const double2*>(d_leg), d_map, map_cstride, nm_, nring_,
-        reinterpret_cast<const double2*>(d_tw_.p), twn_, reinterpret_cast<const double2*>(d_hhat_.p),
+        reinterpret_cast<const double2*>(d_hhat_.p),
         c.rmax, c.Mmax);
     ++launches_;
   }
@@ -634,7 +644,7 @@ void RingFFT::map2leg(const double* d_map, int64_t map_cstride, double* d_leg, i
     dim3 grid((unsigned)c.count, (unsigned)ncomp);
     k_map2leg<<<grid, c.threads, c.smem, stream>>>(
         d_desc_.p, c.first, d_map, map_cstride, reinterpret_cast<double2*>(d_leg), nm_, nring_,
-        reinterpret_cast<const double2*>(d_tw_.p), twn_, reinterpret_cast<const double2*>(d_hhat_.p),
+        reinterpret_cast<const double2*>(d_hhat_.p),
         c.rmax, c.Mmax);
     ++launches_;
   }

@@ -54,11 +54,9 @@ class RingFFT {
   };
   int64_t nring_ = 0, nm_ = 0, npix_ = 0;
   int64_t launches_ = 0;
-  int twn_ = 0;
   std::vector<RingDesc> desc_;
   std::vector<Class> classes_;
   DevBuf<RingDesc> d_desc_;
-  DevBuf<double> d_tw_;     // exp(-2 pi i k / twn), k < twn/2 (re,im)
   DevBuf<double> d_hhat_;   // chirp spectra
 };
 

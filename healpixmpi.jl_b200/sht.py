@@ -166,7 +166,16 @@ def clear_plans() -> None:
 # --------------------------------------------------------------------------------------------
 # the public transforms
 # --------------------------------------------------------------------------------------------
+def _require_colmajor(a, what: str) -> None:
+    """Host arrays must have Julia's memory layout (column-major) — a C-ordered (n, ncomp) numpy array
+    would silently interleave the components."""
+    if isinstance(a, np.ndarray) and a.ndim >= 2 and a.shape[-1] > 1 and not a.flags.f_contiguous:
+        raise _lib.DomainError(_lib.HPSHT_ERR_ARG, f"{what} must be column-major (order='F')")
+
+
 def _checks(d_alm: DAlm, d_map: DMap):
+    _require_colmajor(d_alm.alm, "DAlm.alm")
+    _require_colmajor(d_map.pixels, "DMap.pixels")
     if d_alm.ncomp != d_map.ncomp:
         raise _lib.DomainError(_lib.HPSHT_ERR_ARG, "Number of components must match.")
     if d_alm.info.comm != d_map.info.comm:

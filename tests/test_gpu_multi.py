@@ -1,0 +1,24 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped on the 1-GPU box): the NCCL leg exchange of the
+fused plan, checked by tools/multi_gpu_check.py against the oracle (small sizes) and against a
+single-rank plan (nside 1024), both spins, both directions."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_nccl_ranks_match_single_rank_and_oracle(nranks):
+    import torch
+
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + nranks),
+           os.path.join(ROOT, "tools", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
