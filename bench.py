@@ -199,6 +199,17 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
 
+    # stdout carries exactly one JSON line: route everything else (NCCL banners, library chatter) to
+    # stderr until the final print
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(_saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -218,14 +229,14 @@ def main():
             if i >= args.warmup:
                 tot_ms.append(ms)
         v = float(np.mean(tot_ms))
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": METRIC, "value": v, "unit": "ms", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "FP64 OpenMP CPU port of the same staged algorithm (not ducc; the reference itself "
-                    "needs Julia+MPI+Ducc0 which are absent), bounded sample extrapolated to the full step"}))
+                    "needs Julia+MPI+Ducc0 which are absent), bounded sample extrapolated to the full step"})
         return
 
     import torch
@@ -364,7 +375,7 @@ def main():
                "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline, "stages_ms": stages,
                "fp64_peak_tflops_measured": tf.value}
-        print(json.dumps(out))
+        emit(out)
     plan.destroy()
     if world > 1:
         dist.destroy_process_group()
