@@ -510,6 +510,284 @@ __global__ void k_build_hhat(const int* __restrict__ rs, const int* __restrict__
   for (int k = tid; k < M; k += nt) out[k] = S.A[k];
 }
 
+// ================================================================================================
+// long rings: 4096 < r <= 8192 (nside up to 8192).  The half-complex spectrum of such a ring
+// (2r+1 complex > 227 KB) does not fit one CTA's shared memory, so the transform is split into
+//   leg2map:  k_long_pre  (fold + X->Zc->u|v evaluated on the fly, written to a global scratch)
+//             k_long_fft  (one CTA per half ring: IDFT_r of u or v in shared memory -> pixels)
+//   map2leg:  k_long_fft  (pixels -> conj -> IDFT_r -> conj -> scratch Uhat | Vhat)
+//             k_long_post (Z, X, un-alias and phase shift evaluated on the fly -> leg)
+// IDFT_r in shared memory: r = 8192 (the equatorial belt of nside 8192) is a plain radix-4 FFT; other
+// r use Bluestein with M = 16384, done as one radix-2 decimation step around two 8192-point FFTs so
+// that only 8192 complex values live in shared memory at a time:
+//   forward DIF first stage on the zero-padded input a[0..r), r <= M/2:  lo[i] = a[i], hi[i] = a[i] w_M^i
+//   spectrum halves are multiplied by the matching halves of the chirp spectrum, inverse 8192-point
+//   FFTs give y_lo, y_hi and the wanted outputs are c[j] = y_lo[j] + conj(w_M^j) y_hi[j], j < r.
+// ================================================================================================
+constexpr int LONG_MH = 8192;
+
+// X[k] of the alias-folded, phase-shifted spectrum, evaluated straight from the leg row (k in [0, n/2])
+__device__ __forceinline__ double2 fold_eval(const double2* __restrict__ row, int k, int n, int mmax,
+                                             double phi0) {
+  double ar = 0.0, ai = 0.0;
+  if (k == 0) {
+    ar = row[0].x;
+    for (long long m = n; m <= mmax; m += n) {
+      const double2 t = cmul(row[m], phase((int)m, phi0));
+      ar += 2.0 * t.x;
+    }
+  } else {
+    for (long long m = k; m <= mmax; m += n) {
+      const double2 t = cmul(row[m], phase((int)m, phi0));
+      ar += t.x;
+      ai += t.y;
+    }
+    for (long long m = (long long)n - k; m <= mmax; m += n) {
+      const double2 t = cmul(row[m], phase((int)m, phi0));
+      ar += t.x;
+      ai -= t.y;
+    }
+  }
+  return make_double2(ar, ai);
+}
+
+// Zc[k], 0 <= k < N = 2r, from the folded spectrum
+__device__ __forceinline__ double2 zc_eval(const double2* __restrict__ row, int k, int r, int n, int mmax,
+                                           double phi0, const Roots& W) {
+  const int N = 2 * r;
+  if (k == 0) {
+    const double x0 = fold_eval(row, 0, n, mmax, phi0).x, xn = fold_eval(row, N, n, mmax, phi0).x;
+    return make_double2(x0 + xn, x0 - xn);
+  }
+  if (k == r) {
+    const double2 a = fold_eval(row, r, n, mmax, phi0);
+    return make_double2(2.0 * a.x, -2.0 * a.y);
+  }
+  const double2 A = fold_eval(row, k, n, mmax, phi0), B = cconj(fold_eval(row, N - k, n, mmax, phi0));
+  const double2 Pp = cadd(A, B);
+  const double2 D = cmul(csub(A, B), W(k));
+  return make_double2(Pp.x - D.y, Pp.y + D.x);  // P + i w^k (A - B)
+}
+
+struct LongSmem {
+  double2* A;    // LONG_MH
+  double2* hi;   // n-th roots, n <= 32768: 512 + 2
+  double2* lo;   // 64
+  double2* hi2;  // LONG_MH-th roots: 128 + 2
+  double2* lo2;  // 64
+};
+__device__ __forceinline__ LongSmem carve_long(unsigned char* base, bool with_A) {
+  LongSmem s;
+  double2* p = reinterpret_cast<double2*>(base);
+  s.A = p;
+  p += with_A ? LONG_MH : 0;
+  s.hi = p;
+  p += 514;
+  s.lo = p;
+  p += 64;
+  s.hi2 = p;
+  p += 130;
+  s.lo2 = p;
+  return s;
+}
+size_t long_smem_bytes(bool with_A) { return sizeof(double2) * ((with_A ? LONG_MH : 0) + 514 + 64 + 130 + 64); }
+
+// leg2map, phase 1: u | v of every long ring into the scratch (2r complex per ring and component)
+__global__ void __launch_bounds__(1024) k_long_pre(const RingDesc* __restrict__ desc, int first,
+                                                   const double2* __restrict__ leg, double2* __restrict__ scratch,
+                                                   int64_t scratch_cstride, int64_t nm, int64_t nring) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const RingDesc d = desc[first + blockIdx.x];
+  const int comp = blockIdx.y;
+  const LongSmem S = carve_long(smem_raw, false);
+  const int n = d.nphi, r = d.r;
+  const int mmax = (int)nm - 1;
+  const double2* row = leg + ((int64_t)comp * nring + d.ir) * nm;
+  const Roots W{S.hi, S.lo};
+  build_roots(S.hi, S.lo, n, 1.0, tid, nt);
+  __syncthreads();
+  double2* uv = scratch + (int64_t)comp * scratch_cstride + d.soff;
+  for (int k = tid; k < r; k += nt) {
+    const double2 a = zc_eval(row, k, r, n, mmax, d.phi0, W);
+    const double2 b = zc_eval(row, k + r, r, n, mmax, d.phi0, W);
+    uv[k] = cadd(a, b);
+    uv[k + r] = cmul(csub(a, b), W(2 * k));
+  }
+}
+
+// one half ring: IDFT_r in shared memory.  C2R: scratch u|v -> pixels.  R2C: pixels -> scratch Uhat|Vhat.
+template <bool C2R>
+__global__ void __launch_bounds__(1024) k_long_fft(const RingDesc* __restrict__ desc, int first,
+                                                   double2* __restrict__ scratch, int64_t scratch_cstride,
+                                                   double2* __restrict__ ytmp, int64_t ytmp_cstride,
+                                                   double* __restrict__ map, int64_t map_cstride,
+                                                   const double2* __restrict__ hhat_all) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const RingDesc d = desc[first + (blockIdx.x >> 1)];
+  const int half = blockIdx.x & 1;
+  const int comp = blockIdx.y;
+  const LongSmem S = carve_long(smem_raw, true);
+  const int n = d.nphi, r = d.r;
+  const Roots W{S.hi, S.lo};
+  const Tw TW{S.hi2, S.lo2, LONG_MH};
+  build_roots(S.hi, S.lo, n, 1.0, tid, nt);
+  build_roots(S.hi2, S.lo2, LONG_MH, -1.0, tid, nt);
+  double2* uv = scratch + (int64_t)comp * scratch_cstride + d.soff + (int64_t)half * r;
+  double* px = map + (int64_t)comp * map_cstride + d.pixoff;  // pixel pair (4j+2h, 4j+2h+1) = px2[2j+h]
+  // HEALPix ring starts are multiples of 4 doubles from an even base; fall back to scalar access otherwise
+  const bool al16 = (reinterpret_cast<uintptr_t>(px) & 15) == 0;
+  auto src = [&](int k) -> double2 {
+    if (C2R) return uv[k];
+    if (al16) {
+      const double2 v = reinterpret_cast<const double2*>(px)[2 * k + half];
+      return make_double2(v.x, -v.y);
+    }
+    return make_double2(px[4 * k + 2 * half], -px[4 * k + 2 * half + 1]);
+  };
+  auto dst = [&](int j, double2 v) {
+    if (C2R) {
+      if (al16) {
+        reinterpret_cast<double2*>(px)[2 * j + half] = v;
+      } else {
+        px[4 * j + 2 * half] = v.x;
+        px[4 * j + 2 * half + 1] = v.y;
+      }
+    } else {
+      uv[j] = make_double2(v.x, -v.y);  // conj(IDFT(conj x)) = forward DFT
+    }
+  };
+  __syncthreads();
+  if (d.M == 0) {  // r == LONG_MH: plain power-of-two transform
+    for (int k = tid; k < r; k += nt) S.A[k] = src(k);
+    __syncthreads();
+    fft_dif<true>(S.A, r, TW, tid, nt);
+    bitrev_permute(S.A, r, tid, nt);
+    for (int j = tid; j < r; j += nt) dst(j, S.A[j]);
+    return;
+  }
+  // Bluestein, M = 2 * LONG_MH
+  const int two_r = 2 * r;
+  const double2* hh = hhat_all + d.hoff;
+  double2* y0 = ytmp + (int64_t)comp * ytmp_cstride + d.yoff + (int64_t)half * LONG_MH;
+  const double invM = 1.0 / (double)(2 * LONG_MH);
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int k = tid; k < LONG_MH; k += nt) {
+      double2 v = make_double2(0.0, 0.0);
+      if (k < r) {
+        const int q = (int)(((unsigned)k * (unsigned)k) % (unsigned)two_r);
+        v = cmul(src(k), W(2 * q));
+        if (pass == 1) {  // times w_M^k = exp(-2 pi i k / M)
+          double s, c;
+          sincospi(2.0 * (double)k * invM, &s, &c);
+          v = cmul(v, make_double2(c, -s));
+        }
+      }
+      S.A[k] = v;
+    }
+    __syncthreads();
+    fft_dif<false>(S.A, LONG_MH, TW, tid, nt);
+    for (int k = tid; k < LONG_MH; k += nt) S.A[k] = cmul(S.A[k], __ldg(&hh[pass * LONG_MH + k]));
+    __syncthreads();
+    fft_dit<true>(S.A, LONG_MH, TW, tid, nt);
+    if (pass == 0) {
+      for (int j = tid; j < r; j += nt) y0[j] = S.A[j];
+      __syncthreads();
+    }
+  }
+  for (int j = tid; j < r; j += nt) {
+    double s, c;
+    sincospi(2.0 * (double)j * invM, &s, &c);
+    const double2 cj = cadd(y0[j], cmul(S.A[j], make_double2(c, s)));  // y_lo + conj(w_M^j) y_hi
+    const int q = (int)(((unsigned)j * (unsigned)j) % (unsigned)two_r);
+    dst(j, cmul(cj, W(2 * q)));
+  }
+}
+
+// map2leg, final phase: leg[m] = exp(-i m phi0) Xt[m mod n] with X evaluated from Uhat | Vhat on the fly
+__global__ void __launch_bounds__(1024) k_long_post(const RingDesc* __restrict__ desc, int first,
+                                                    const double2* __restrict__ scratch, int64_t scratch_cstride,
+                                                    double2* __restrict__ leg, int64_t nm, int64_t nring) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const RingDesc d = desc[first + blockIdx.x];
+  const int comp = blockIdx.y;
+  const LongSmem S = carve_long(smem_raw, false);
+  const int n = d.nphi, r = d.r, N = 2 * r;
+  const int mmax = (int)nm - 1;
+  double2* row = leg + ((int64_t)comp * nring + d.ir) * nm;
+  const Roots W{S.hi, S.lo};
+  build_roots(S.hi, S.lo, n, 1.0, tid, nt);
+  __syncthreads();
+  const double2* uv = scratch + (int64_t)comp * scratch_cstride + d.soff;
+  auto Z = [&](int k) -> double2 {  // k in [0, N]; Z[N] = Z[0]
+    if (k >= N) k -= N;
+    const int kk = k < r ? k : k - r;
+    const double2 t = cmulc(uv[r + kk], W(2 * kk));  // conj(w)^{2kk} Vhat
+    return k < r ? cadd(uv[kk], t) : csub(uv[kk], t);
+  };
+  for (int m = tid; m <= mmax; m += nt) {
+    const int km = m % n;
+    const bool up = km > N;
+    const int k = up ? n - km : km;
+    const double2 A = Z(k), B = cconj(Z(N - k));
+    const double2 Pp = make_double2(0.5 * (A.x + B.x), 0.5 * (A.y + B.y));
+    const double2 D = cmulc(csub(A, B), W(k == N ? 0 : k));
+    // conj(w)^N = -1: fold the sign into D for k == N
+    const double sg = (k == N) ? -1.0 : 1.0;
+    const double2 X = make_double2(Pp.x + sg * 0.5 * D.y, Pp.y - sg * 0.5 * D.x);  // P - i/2 conj(w^k)(A-B)
+    const double2 v = up ? cconj(X) : X;
+    row[m] = cmulc(v, phase(m, d.phi0));
+  }
+}
+
+// chirp spectrum for the long Bluestein (M = 2 LONG_MH): the two halves of the first DIF stage
+__global__ void __launch_bounds__(1024) k_build_hhat_long(const int* __restrict__ rs,
+                                                          const int64_t* __restrict__ hoffs,
+                                                          double2* __restrict__ hhat_all) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const LongSmem S = carve_long(smem_raw, true);
+  const int r = rs[blockIdx.x];
+  const int n = 4 * r;
+  const int M = 2 * LONG_MH;
+  const Roots W{S.hi, S.lo};
+  const Tw TW{S.hi2, S.lo2, LONG_MH};
+  build_roots(S.hi, S.lo, n, 1.0, tid, nt);
+  build_roots(S.hi2, S.lo2, LONG_MH, -1.0, tid, nt);
+  __syncthreads();
+  const double inv = 1.0 / (double)M;
+  auto h = [&](int k) -> double2 {  // h[k], k in [0, M): conj(c[|d|]) / M circularly for |d| < r
+    int dd = -1;
+    if (k < r)
+      dd = k;
+    else if (k > M - r)
+      dd = M - k;
+    if (dd < 0) return make_double2(0.0, 0.0);
+    const int q = (int)(((unsigned)dd * (unsigned)dd) % (unsigned)(2 * r));
+    const double2 c = W(2 * q);
+    return make_double2(c.x * inv, -c.y * inv);
+  };
+  double2* out = hhat_all + hoffs[blockIdx.x];
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int k = tid; k < LONG_MH; k += nt) {
+      const double2 a = h(k), b = h(k + LONG_MH);
+      if (pass == 0) {
+        S.A[k] = cadd(a, b);
+      } else {
+        double s, c;
+        sincospi(2.0 * (double)k * inv, &s, &c);
+        S.A[k] = cmul(csub(a, b), make_double2(c, -s));
+      }
+    }
+    __syncthreads();
+    fft_dif<false>(S.A, LONG_MH, TW, tid, nt);
+    for (int k = tid; k < LONG_MH; k += nt) out[pass * LONG_MH + k] = S.A[k];
+    __syncthreads();
+  }
+}
+
 int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -529,13 +807,15 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
   std::map<int, int64_t> hoff_of_r;
   std::vector<int> rs, Ms;
   std::vector<int64_t> hoffs;
-  int64_t htotal = 0;
+  std::vector<int> rs_long;
+  std::vector<int64_t> hoffs_long;
+  int64_t htotal = 0, scratch_total = 0, ytmp_total = 0;
+  desc_long_.clear();
   for (int64_t i = 0; i < nring; ++i) {
     const int64_t n = nphi[i];
     HP_REQUIRE(n >= 4 && n % 4 == 0, HPSHT_ERR_UNSUPPORTED,
                "ring length must be a positive multiple of 4 (HEALPix rings always are)");
-    HP_REQUIRE(n / 4 <= 4096, HPSHT_ERR_UNSUPPORTED,
-               "ring length > 16384 (nside > 4096) needs the multi-CTA FFT path, not built yet");
+    HP_REQUIRE(n / 4 <= 8192, HPSHT_ERR_UNSUPPORTED, "ring length > 32768 (nside > 8192) is not supported");
     npix_ += n;
     RingDesc d;
     d.pixoff = ringstart[i];
@@ -544,6 +824,31 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     d.nphi = (int)n;
     d.r = (int)(n / 4);
     const bool pow2 = (d.r & (d.r - 1)) == 0;
+    d.soff = d.yoff = -1;
+    if (d.r > 4096) {  // long ring: split transform through a global scratch (see k_long_*)
+      d.soff = scratch_total;
+      scratch_total += 2 * (int64_t)d.r;
+      if (pow2) {
+        d.M = 0;
+        d.hoff = -1;
+      } else {
+        d.M = 2 * LONG_MH;
+        d.yoff = ytmp_total;
+        ytmp_total += 2 * (int64_t)LONG_MH;
+        auto it = hoff_of_r.find(d.r);
+        if (it == hoff_of_r.end()) {
+          hoff_of_r[d.r] = htotal;
+          rs_long.push_back(d.r);
+          hoffs_long.push_back(htotal);
+          d.hoff = htotal;
+          htotal += d.M;
+        } else {
+          d.hoff = it->second;
+        }
+      }
+      desc_long_.push_back(d);
+      continue;
+    }
     if (pow2) {
       d.M = 0;
       d.hoff = -1;
@@ -595,11 +900,27 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     i = j;
   }
   d_desc_.upload(desc_.data(), desc_.size(), stream);
+  if (!desc_long_.empty()) {
+    // biggest rings first
+    std::stable_sort(desc_long_.begin(), desc_long_.end(),
+                     [](const RingDesc& a, const RingDesc& b) { return a.r > b.r; });
+    d_desc_long_.upload(desc_long_.data(), desc_long_.size(), stream);
+    scratch_cstride_ = scratch_total;
+    ytmp_cstride_ = ytmp_total;
+    HP_CUDA(cudaFuncSetAttribute(k_long_fft<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)long_smem_bytes(true)));
+    HP_CUDA(cudaFuncSetAttribute(k_long_fft<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)long_smem_bytes(true)));
+    HP_CUDA(cudaFuncSetAttribute(k_build_hhat_long, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)long_smem_bytes(true)));
+  }
   size_t max_smem = 0;
   for (auto& c : classes_) max_smem = std::max(max_smem, c.smem);
   HP_REQUIRE(max_smem <= 227 * 1024, HPSHT_ERR_UNSUPPORTED, "ring too long for the in-smem FFT");
-  HP_CUDA(cudaFuncSetAttribute(k_leg2map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-  HP_CUDA(cudaFuncSetAttribute(k_map2leg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  if (max_smem > 0) {
+    HP_CUDA(cudaFuncSetAttribute(k_leg2map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    HP_CUDA(cudaFuncSetAttribute(k_map2leg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  }
   // chirp spectra
   d_hhat_.alloc((size_t)std::max<int64_t>(htotal, 1) * 2);
   if (!rs.empty()) {
@@ -622,7 +943,23 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     HP_CUDA(cudaGetLastError());
     HP_CUDA(cudaStreamSynchronize(stream));
   }
+  if (!rs_long.empty()) {
+    DevBuf<int> d_rs;
+    DevBuf<int64_t> d_hoffs;
+    d_rs.upload(rs_long.data(), rs_long.size(), stream);
+    d_hoffs.upload(hoffs_long.data(), hoffs_long.size(), stream);
+    k_build_hhat_long<<<(unsigned)rs_long.size(), 1024, long_smem_bytes(true), stream>>>(
+        d_rs.p, d_hoffs.p, reinterpret_cast<double2*>(d_hhat_.p));
+    HP_CUDA(cudaGetLastError());
+    HP_CUDA(cudaStreamSynchronize(stream));
+  }
   HP_CUDA(cudaStreamSynchronize(stream));
+}
+
+void RingFFT::ensure_long_scratch(int ncomp) {
+  if (desc_long_.empty()) return;
+  d_scratch_.ensure((size_t)scratch_cstride_ * 2 * ncomp);
+  if (ytmp_cstride_ > 0) d_ytmp_.ensure((size_t)ytmp_cstride_ * 2 * ncomp);
 }
 
 void RingFFT::leg2map(const double* d_leg, double* d_map, int64_t map_cstride, int ncomp,
@@ -634,6 +971,18 @@ void RingFFT::leg2map(const double* d_leg, double* d_map, int64_t map_cstride, i
         reinterpret_cast<const double2*>(d_hhat_.p),
         c.rmax, c.Mmax);
     ++launches_;
+  }
+  if (!desc_long_.empty()) {
+    ensure_long_scratch(ncomp);
+    const unsigned nl = (unsigned)desc_long_.size();
+    k_long_pre<<<dim3(nl, (unsigned)ncomp), 1024, long_smem_bytes(false), stream>>>(
+        d_desc_long_.p, 0, reinterpret_cast<const double2*>(d_leg), reinterpret_cast<double2*>(d_scratch_.p),
+        scratch_cstride_, nm_, nring_);
+    k_long_fft<true><<<dim3(2 * nl, (unsigned)ncomp), 1024, long_smem_bytes(true), stream>>>(
+        d_desc_long_.p, 0, reinterpret_cast<double2*>(d_scratch_.p), scratch_cstride_,
+        reinterpret_cast<double2*>(d_ytmp_.p), ytmp_cstride_, d_map, map_cstride,
+        reinterpret_cast<const double2*>(d_hhat_.p));
+    launches_ += 2;
   }
   HP_CUDA(cudaGetLastError());
 }
@@ -647,6 +996,18 @@ void RingFFT::map2leg(const double* d_map, int64_t map_cstride, double* d_leg, i
         reinterpret_cast<const double2*>(d_hhat_.p),
         c.rmax, c.Mmax);
     ++launches_;
+  }
+  if (!desc_long_.empty()) {
+    ensure_long_scratch(ncomp);
+    const unsigned nl = (unsigned)desc_long_.size();
+    k_long_fft<false><<<dim3(2 * nl, (unsigned)ncomp), 1024, long_smem_bytes(true), stream>>>(
+        d_desc_long_.p, 0, reinterpret_cast<double2*>(d_scratch_.p), scratch_cstride_,
+        reinterpret_cast<double2*>(d_ytmp_.p), ytmp_cstride_, const_cast<double*>(d_map), map_cstride,
+        reinterpret_cast<const double2*>(d_hhat_.p));
+    k_long_post<<<dim3(nl, (unsigned)ncomp), 1024, long_smem_bytes(false), stream>>>(
+        d_desc_long_.p, 0, reinterpret_cast<const double2*>(d_scratch_.p), scratch_cstride_,
+        reinterpret_cast<double2*>(d_leg), nm_, nring_);
+    launches_ += 2;
   }
   HP_CUDA(cudaGetLastError());
 }

@@ -23,6 +23,8 @@ struct RingDesc {
   int nphi;         // ring length n = 4 r
   int r;
   int M;            // Bluestein convolution length (power of two >= 2r-1), 0 for power-of-two r
+  int64_t soff;     // long rings (r > 4096): offset of the ring's u|v block in the scratch, else -1
+  int64_t yoff;     // long Bluestein rings: offset of the ring's y_lo block in the second scratch, else -1
 };
 
 class RingFFT {
@@ -54,7 +56,11 @@ class RingFFT {
   };
   int64_t nring_ = 0, nm_ = 0, npix_ = 0;
   int64_t launches_ = 0;
-  std::vector<RingDesc> desc_;
+  void ensure_long_scratch(int ncomp);
+  std::vector<RingDesc> desc_, desc_long_;
+  DevBuf<RingDesc> d_desc_long_;
+  DevBuf<double> d_scratch_, d_ytmp_;
+  int64_t scratch_cstride_ = 0, ytmp_cstride_ = 0;
   std::vector<Class> classes_;
   DevBuf<RingDesc> d_desc_;
   DevBuf<double> d_hhat_;   // chirp spectra

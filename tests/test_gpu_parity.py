@@ -162,6 +162,30 @@ def test_ring_fft_lengths(H, O):
         assert max(per) < 2e-13, (nm, int(rs[int(np.argmax(per))]), max(per))
 
 
+def test_long_rings(H, O):
+    """Rings with 4096 < r <= 8192 (nside up to 8192) take the split transform through a global
+    scratch: power of two (8192), prime (8191), composite lengths, both directions, with and without
+    aliasing, two components."""
+    rng = np.random.default_rng(11)
+    for rs, nm in (([4097, 5000, 6144, 8191, 8192, 3, 4096], 301), ([4097], 20000)):
+        rs = np.array(rs)
+        nphi = 4 * rs
+        rstart0 = np.concatenate([[0], np.cumsum(nphi)[:-1]]).astype(np.int64)
+        phi0 = rng.uniform(0, 0.3, len(rs))
+        npix = int(nphi.sum())
+        ncomp = 2 if nm < 1000 else 1
+        leg = _rand_alm(rng, ncomp, len(rs) * nm).reshape(ncomp, len(rs), nm)
+        got = _stage_leg2map(H, leg, nphi, phi0, rstart0, npix)
+        ref = O.leg2map(leg, nphi, phi0, rstart0, npix).astype(np.float64)
+        per = [rel_l2(got[:, a:a + n], ref[:, a:a + n]) for a, n in zip(rstart0, nphi)]
+        assert max(per) < 2e-13, (nm, per)
+        mp = rng.standard_normal((ncomp, npix))
+        g2 = _stage_map2leg(H, mp, nm, nphi, phi0, rstart0)
+        r2 = O.map2leg(mp, nm, nphi, phi0, rstart0).astype(np.complex128)
+        per = [rel_l2(g2[:, i], r2[:, i]) for i in range(len(rs))]
+        assert max(per) < 2e-13, (nm, per)
+
+
 def _fused(H, O, nside, lmax, spin, seed, device=False):
     import healpixmpi_jl_b200 as Hm
 
@@ -388,3 +412,29 @@ def test_large_size_properties(H, O):
         w = nphi[~polar].astype(float)
         assert np.sqrt(np.sum(w * per[~polar] ** 2) / np.sum(w)) < 1e-12, per
         plan.destroy()
+
+
+def test_config5_nside8192_adjointness(H, O):
+    """BASELINE config 5 (spin-0 adjoint at nside 8192, lmax 16383; rings of up to 32768 pixels take the
+    long-ring FFT path): the adjointness identity <f, Y a> = <Y^T f, a>_w at full size, device resident."""
+    import torch
+
+    import healpixmpi_jl_b200 as Hm
+
+    nside, lmax = 8192, 16383
+    plan = Hm.Plan(nside, lmax, Hm.COMM_SELF, 1)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    f = torch.randn((1, plan.npix_loc), dtype=torch.float64, device="cuda", generator=g)
+    a = torch.randn((1, plan.nalm_loc, 2), dtype=torch.float64, device="cuda", generator=g)
+    a[0, :lmax + 1, 1] = 0.0
+    out_a, out_m = torch.empty_like(a), torch.empty_like(f)
+    plan.adjoint_alm2map(f, out_a, 1)
+    plan.alm2map(a, out_m, 1)
+    w = torch.full((plan.nalm_loc,), 2.0, dtype=torch.float64, device="cuda")
+    w[:lmax + 1] = 1.0
+    lhs = float((f * out_m).sum())
+    rhs = float((w * (out_a[0, :, 0] * a[0, :, 0] + out_a[0, :, 1] * a[0, :, 1])).sum())
+    assert abs(lhs - rhs) <= 1e-12 * float(f.norm()) * float(out_m.norm()), (lhs, rhs)
+    sc, sd = plan.legendre_steps(0)
+    assert abs(sc / 1.7409e12 - 1) < 1e-3  # SURVEY 8d work model
+    plan.destroy()
