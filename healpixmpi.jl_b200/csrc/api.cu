@@ -34,28 +34,39 @@ void require_device() {
 }
 
 // ---- exchange pack / unpack (map-side leg <-> per-peer blocks) ----
-// legF[(comp*nr_loc + j)*nm_tot + (s + P*i)]  <->  blk_s[(comp*nr_loc + j)*nm_s + i]
+// legF[(comp*nr_loc + j)*nm_tot + m]  <->  block of source s = m % P, laid out [m-slab][comp][ring][m in slab]:
+//   boff[s] + nr_loc*(ncs*sstart + comp*nms) + j*nms + (i - sstart),   i = m / P (local m index on s),
+//   slabs of K-th parts of s's nm_s local m's (ms = ceil(nm_s / K)).
+struct ExchGeom {
+  int64_t nm_tot, nr_loc, mmax;
+  int P, K, ncs;
+};
+__device__ __forceinline__ int64_t mapside_off(const ExchGeom& g, const int64_t* boff, int64_t m, int64_t j, int comp) {
+  const int s = (int)(m % g.P);
+  const int64_t i = m / g.P;
+  const int64_t nm_s = (g.mmax + g.P - s) / g.P;
+  const int64_t ms = (nm_s + g.K - 1) / g.K;
+  const int64_t ss = (i / ms) * ms;
+  const int64_t ns = min(ms, nm_s - ss);
+  return boff[s] + g.nr_loc * ((int64_t)g.ncs * ss + (int64_t)comp * ns) + j * ns + (i - ss);
+}
 __global__ void k_unpack(const double2* __restrict__ mapside, const int64_t* __restrict__ boff,
-                         double2* __restrict__ legF, int64_t nm_tot, int64_t nr_loc, int ncomp, int P,
-                         int64_t mmax) {
+                         double2* __restrict__ legF, ExchGeom g) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = blockIdx.y;  // comp*nr_loc + j
-  if (m >= nm_tot) return;
-  const int s = (int)(m % P);
-  const int64_t i = m / P;
-  const int64_t nm_s = (mmax + P - s) / P;
-  legF[row * nm_tot + m] = mapside[boff[s] + row * nm_s + i];
+  if (m >= g.nm_tot) return;
+  const int comp = (int)(row / g.nr_loc);
+  const int64_t j = row % g.nr_loc;
+  legF[row * g.nm_tot + m] = mapside[mapside_off(g, boff, m, j, comp)];
 }
 __global__ void k_pack(const double2* __restrict__ legF, const int64_t* __restrict__ boff,
-                       double2* __restrict__ mapside, int64_t nm_tot, int64_t nr_loc, int ncomp, int P,
-                       int64_t mmax) {
+                       double2* __restrict__ mapside, ExchGeom g) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t row = blockIdx.y;
-  if (m >= nm_tot) return;
-  const int s = (int)(m % P);
-  const int64_t i = m / P;
-  const int64_t nm_s = (mmax + P - s) / P;
-  mapside[boff[s] + row * nm_s + i] = legF[row * nm_tot + m];
+  if (m >= g.nm_tot) return;
+  const int comp = (int)(row / g.nr_loc);
+  const int64_t j = row % g.nr_loc;
+  mapside[mapside_off(g, boff, m, j, comp)] = legF[row * g.nm_tot + m];
 }
 
 // ---- FP64 FMA peak probe: 8 independent chains per thread, no memory traffic ----
@@ -108,7 +119,12 @@ struct hpsht_plan {
   int64_t nm_loc = 0, nalm_loc = 0, nr_loc = 0, npix_loc = 0, nr_tot = 0, nm_tot = 0;
   bool stages_ready = false;
 
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // compute
+  cudaStream_t cstream = nullptr;  // NCCL exchange (overlaps the Legendre work of the next m-slab)
+  int K = 1;                       // m-slabs per rank
+  std::vector<cudaEvent_t> ev_slab, ev_done;
+  std::vector<cudaStream_t> sstream;  // one per m-slab: adjoint slab kernels run concurrently (no wave tails)
+  cudaEvent_t ev_ready = nullptr;
   LegendreStage leg;
   RingFFT fft;
   DevBuf<double> legF;      // map-side leg [ncomp][nr_loc][nm_tot] (complex)
@@ -124,7 +140,9 @@ struct hpsht_plan {
 
   void build_shard();
   void ensure_stages();
-  void exchange(bool synthesis, int ncomp);
+  void exchange_slab(bool synthesis, int ncomp, int slab, cudaStream_t st);
+  int64_t slab_start(int q, int slab) const;
+  int64_t slab_size(int q, int slab) const;
   void run(bool synthesis, const double* in, double* out, int ncomp);
 };
 
@@ -169,21 +187,40 @@ void hpsht_plan::build_shard() {
   }
 }
 
+// m-slab `slab` of rank q: local m indices [slab_start, slab_start + slab_size)
+int64_t hpsht_plan::slab_start(int q, int slab) const {
+  const int64_t ms = (nm_of[(size_t)q] + K - 1) / K;
+  return std::min<int64_t>((int64_t)slab * ms, nm_of[(size_t)q]);
+}
+int64_t hpsht_plan::slab_size(int q, int slab) const {
+  const int64_t ms = (nm_of[(size_t)q] + K - 1) / K;
+  const int64_t ss = slab_start(q, slab);
+  return std::max<int64_t>(0, std::min<int64_t>(ms, nm_of[(size_t)q] - ss));
+}
+
 void hpsht_plan::ensure_stages() {
   if (stages_ready) return;
   // ---- leg layout seen by the Legendre kernels: ring slots in thetatot order ----
   LegLayout lay;
-  lay.base.resize((size_t)nr_tot);
-  lay.mstride.assign((size_t)nr_tot, 1);
-  lay.cstride.resize((size_t)nr_tot);
+  lay.a0.resize((size_t)nr_tot);
+  lay.nr.resize((size_t)nr_tot);
+  lay.j.resize((size_t)nr_tot);
   if (P == 1) {
     // single rank: the Legendre stage reads/writes the map-side array directly (src/sht.jl:87-88)
+    K = 1;
     for (int64_t s = 0; s < nr_tot; ++s) {
-      lay.base[(size_t)s] = s * nm_tot;
-      lay.cstride[(size_t)s] = nr_loc * nm_tot;
+      lay.a0[(size_t)s] = 0;
+      lay.nr[(size_t)s] = nr_loc;
+      lay.j[(size_t)s] = s;
     }
     legF.alloc((size_t)max_ncomp * nr_loc * nm_tot * 2);
   } else {
+    // m-slabs: K > 1 overlaps the exchange of one slab with the Legendre work of the next.  Measured on
+    // 2 and 8 B200 at nside 4096 (profiles/r01_scaling_slabs.md) the exchange is 3-8 % of a transform
+    // and the extra kernel tails of K = 2..8 cost more than the overlap hides, so the default is 1.
+    const char* ek = getenv("HPSHT_NSLAB");
+    K = ek ? std::max(1, atoi(ek)) : 1;
+    K = (int)std::min<int64_t>(K, nm_loc);
     aoff.assign((size_t)P + 1, 0);
     boff.assign((size_t)P + 1, 0);
     for (int t = 0; t < P; ++t) {
@@ -193,48 +230,69 @@ void hpsht_plan::ensure_stages() {
     int64_t s = 0;
     for (int t = 0; t < P; ++t)
       for (int64_t j = 0; j < nr_of[(size_t)t]; ++j, ++s) {
-        lay.base[(size_t)s] = aoff[(size_t)t] + j * nm_loc;
-        lay.cstride[(size_t)s] = nr_of[(size_t)t] * nm_loc;
+        lay.a0[(size_t)s] = aoff[(size_t)t];
+        lay.nr[(size_t)s] = nr_of[(size_t)t];
+        lay.j[(size_t)s] = j;
       }
+    lay.sstart.resize((size_t)nm_loc);
+    lay.nms.resize((size_t)nm_loc);
+    for (int sl = 0; sl < K; ++sl)
+      for (int64_t i = slab_start(rank, sl); i < slab_start(rank, sl) + slab_size(rank, sl); ++i) {
+        lay.sstart[(size_t)i] = slab_start(rank, sl);
+        lay.nms[(size_t)i] = slab_size(rank, sl);
+      }
+    lay.ncs = max_ncomp;
     almside.alloc((size_t)aoff[(size_t)P] * 2);
     mapside.alloc((size_t)boff[(size_t)P] * 2);
     legF.alloc((size_t)max_ncomp * nr_loc * nm_tot * 2);
     d_boff.upload(boff.data(), boff.size(), stream);
+    HP_CUDA(cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking));
+    ev_slab.resize((size_t)K);
+    for (auto& e : ev_slab) HP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev_done.resize((size_t)K);
+    for (auto& e : ev_done) HP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    sstream.resize((size_t)K);
+    for (auto& st : sstream) HP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    HP_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
   }
   leg.setup(lmax, mval.data(), mstart.data(), nm_loc, nr_tot, thetatot.data(), lay, max_ncomp, stream);
+  HP_REQUIRE(P == 1 || leg.nslabs() == K, HPSHT_ERR_INTERNAL, "slab count mismatch");
   fft.setup(nr_loc, nphi.data(), phi0.data(), rstart.data(), nm_tot, stream);
   HP_CUDA(cudaStreamSynchronize(stream));
   stages_ready = true;
 }
 
 // m-sharded <-> ring-sharded transpose of the leg array (communicate_alm2map! / communicate_map2alm!,
-// src/sht.jl:5-44,106-135), all components in one grouped NCCL send/recv exchange.
-void hpsht_plan::exchange(bool synthesis, int ncomp) {
+// src/sht.jl:5-44,106-135), one m-slab at a time: all components of the slab in one grouped NCCL
+// send/recv exchange.  Per peer t the slab piece is contiguous on both sides.
+void hpsht_plan::exchange_slab(bool synthesis, int ncomp, int slab, cudaStream_t st) {
   NcclApi& N = NcclApi::get();
   double* A = almside.p;
   double* B = mapside.p;
+  const int64_t my_ss = slab_start(rank, slab), my_ns = slab_size(rank, slab);
   HP_NCCL(N.GroupStart());
   for (int t = 0; t < P; ++t) {
-    const size_t na = (size_t)ncomp * nr_of[(size_t)t] * nm_loc * 2;  // doubles, alm-side block t
-    const size_t nb = (size_t)ncomp * nr_loc * nm_of[(size_t)t] * 2;  // doubles, map-side block t
-    double* pa = A + (size_t)aoff[(size_t)t] * 2;
-    double* pb = B + (size_t)boff[(size_t)t] * 2;
     if (t == rank) continue;
+    // alm-side: my m-slab x t's rings ; map-side: t's m-slab x my rings
+    const size_t na = (size_t)ncomp * nr_of[(size_t)t] * my_ns * 2;
+    const size_t nb = (size_t)ncomp * nr_loc * slab_size(t, slab) * 2;
+    double* pa = A + ((size_t)aoff[(size_t)t] + (size_t)max_ncomp * nr_of[(size_t)t] * my_ss) * 2;
+    double* pb = B + ((size_t)boff[(size_t)t] + (size_t)max_ncomp * nr_loc * slab_start(t, slab)) * 2;
     if (synthesis) {
-      HP_NCCL(N.Send(pa, na, ncclDouble, t, comm, stream));
-      HP_NCCL(N.Recv(pb, nb, ncclDouble, t, comm, stream));
+      if (na) HP_NCCL(N.Send(pa, na, ncclDouble, t, comm, st));
+      if (nb) HP_NCCL(N.Recv(pb, nb, ncclDouble, t, comm, st));
     } else {
-      HP_NCCL(N.Send(pb, nb, ncclDouble, t, comm, stream));
-      HP_NCCL(N.Recv(pa, na, ncclDouble, t, comm, stream));
+      if (nb) HP_NCCL(N.Send(pb, nb, ncclDouble, t, comm, st));
+      if (na) HP_NCCL(N.Recv(pa, na, ncclDouble, t, comm, st));
     }
   }
   HP_NCCL(N.GroupEnd());
-  {  // own block never leaves the device
-    const size_t n = (size_t)ncomp * nr_loc * nm_loc * 2;
-    double* pa = A + (size_t)aoff[(size_t)rank] * 2;
-    double* pb = B + (size_t)boff[(size_t)rank] * 2;
+  if (my_ns > 0) {  // own block never leaves the device
+    const size_t n = (size_t)ncomp * nr_loc * my_ns * 2;
+    double* pa = A + ((size_t)aoff[(size_t)rank] + (size_t)max_ncomp * nr_loc * my_ss) * 2;
+    double* pb = B + ((size_t)boff[(size_t)rank] + (size_t)max_ncomp * nr_loc * my_ss) * 2;
     HP_CUDA(cudaMemcpyAsync(synthesis ? pb : pa, synthesis ? pa : pb, n * sizeof(double),
-                            cudaMemcpyDeviceToDevice, stream));
+                            cudaMemcpyDeviceToDevice, st));
   }
 }
 
@@ -268,6 +326,13 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
   }
   HP_CUDA(cudaEventRecord(e[1], stream));
   const int TB = 256;
+  ExchGeom G;
+  G.nm_tot = nm_tot;
+  G.nr_loc = nr_loc;
+  G.mmax = lmax;
+  G.P = P;
+  G.K = K;
+  G.ncs = max_ncomp;
   if (synthesis) {
     // alm2leg (src/sht.jl:85)
     if (P == 1) {
@@ -275,15 +340,23 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
       HP_CUDA(cudaEventRecord(e[2], stream));
       HP_CUDA(cudaEventRecord(e[3], stream));
     } else {
-      leg.alm2leg(d_in, nalm_loc, almside.p, aoff[(size_t)P], ncomp, stream);
-      HP_CUDA(cudaEventRecord(e[2], stream));
-      exchange(true, ncomp);  // src/sht.jl:90
+      // slab s is exchanged on the communication stream while slab s+1 is computed (src/sht.jl:90)
+      leg.alm2leg_begin(d_in, nalm_loc, almside.p, aoff[(size_t)P], ncomp, stream);
+      for (int s = 0; s < K; ++s) {
+        leg.alm2leg_slab(s, almside.p, ncomp, stream);
+        HP_CUDA(cudaEventRecord(ev_slab[(size_t)s], stream));
+        HP_CUDA(cudaStreamWaitEvent(cstream, ev_slab[(size_t)s], 0));
+        exchange_slab(true, ncomp, s, cstream);
+      }
+      HP_CUDA(cudaEventRecord(e[2], stream));  // end of the Legendre kernels
+      HP_CUDA(cudaEventRecord(ev_ready, cstream));
+      HP_CUDA(cudaStreamWaitEvent(stream, ev_ready, 0));
       dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nr_loc));
       k_unpack<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(mapside.p), d_boff.p,
-                                        reinterpret_cast<double2*>(legF.p), nm_tot, nr_loc, ncomp, P, lmax);
+                                        reinterpret_cast<double2*>(legF.p), G);
       HP_CUDA(cudaGetLastError());
-      extra += 2;
-      HP_CUDA(cudaEventRecord(e[3], stream));
+      extra += 1 + K;
+      HP_CUDA(cudaEventRecord(e[3], stream));  // exposed (non-overlapped) exchange tail + unpack
     }
     // leg2map (src/sht.jl:93)
     fft.leg2map(legF.p, d_out, npix_loc, ncomp, stream);
@@ -298,12 +371,31 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
     } else {
       dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nr_loc));
       k_pack<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(legF.p), d_boff.p,
-                                      reinterpret_cast<double2*>(mapside.p), nm_tot, nr_loc, ncomp, P, lmax);
+                                      reinterpret_cast<double2*>(mapside.p), G);
       HP_CUDA(cudaGetLastError());
-      extra += 2;
-      exchange(false, ncomp);  // src/sht.jl:174
-      HP_CUDA(cudaEventRecord(e[3], stream));
-      leg.leg2alm(almside.p, d_out, nalm_loc, ncomp, stream);
+      extra += 1 + K;
+      HP_CUDA(cudaEventRecord(ev_ready, stream));
+      HP_CUDA(cudaStreamWaitEvent(cstream, ev_ready, 0));
+      leg.leg2alm_begin(ncomp, stream);
+      for (int s = 0; s < K; ++s) {  // src/sht.jl:174, slab by slab
+        exchange_slab(false, ncomp, s, cstream);
+        HP_CUDA(cudaEventRecord(ev_slab[(size_t)s], cstream));
+      }
+      // every slab's kernel starts as soon as its data has landed; the slab kernels run on their own
+      // streams so that the tail of one slab overlaps the head of the next
+      HP_CUDA(cudaEventRecord(ev_ready, stream));  // leg2alm_begin (buffer setup) done
+      for (int s = 0; s < K; ++s) {
+        cudaStream_t st = sstream[(size_t)s];
+        HP_CUDA(cudaStreamWaitEvent(st, ev_ready, 0));
+        HP_CUDA(cudaStreamWaitEvent(st, ev_slab[(size_t)s], 0));
+        leg.leg2alm_slab(s, almside.p, ncomp, st);
+        HP_CUDA(cudaEventRecord(ev_done[(size_t)s], st));
+      }
+      HP_CUDA(cudaStreamWaitEvent(stream, ev_slab[0], 0));
+      HP_CUDA(cudaEventRecord(e[3], stream));  // exposed exchange: pack + first slab
+      for (int s = 0; s < K; ++s) HP_CUDA(cudaStreamWaitEvent(stream, ev_done[(size_t)s], 0));
+      leg.mark_main_end(stream);
+      leg.leg2alm_end(d_out, nalm_loc, ncomp, stream);
     }
     HP_CUDA(cudaEventRecord(e[4], stream));
   }
@@ -312,6 +404,7 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
                             cudaMemcpyDeviceToHost, stream));
   HP_CUDA(cudaEventRecord(e[5], stream));
   HP_CUDA(cudaStreamSynchronize(stream));
+  if (cstream) HP_CUDA(cudaStreamSynchronize(cstream));
   auto el = [&](int a, int b) {
     float f = 0;
     cudaEventElapsedTime(&f, e[a], e[b]);
@@ -381,10 +474,10 @@ LegendreStage& get_leg_stage(StageCache& c, int64_t lmax, int64_t nm, const int6
   if (!c.leg || !(c.lkey == k)) {
     c.leg.reset(new LegendreStage());
     LegLayout lay;  // reference alm-side layout (nm, nring, ncomp): leg[(comp*nring + ir)*nm + mi]
-    lay.base.resize((size_t)nring);
-    lay.mstride.assign((size_t)nring, 1);
-    lay.cstride.assign((size_t)nring, nring * nm);
-    for (int64_t s = 0; s < nring; ++s) lay.base[(size_t)s] = s * nm;
+    lay.a0.assign((size_t)nring, 0);
+    lay.nr.assign((size_t)nring, nring);
+    lay.j.resize((size_t)nring);
+    for (int64_t s = 0; s < nring; ++s) lay.j[(size_t)s] = s;
     c.leg->setup(lmax, mval, mstart, nm, nring, theta, lay, 2, 0);
     c.lkey = k;
   }
@@ -698,6 +791,15 @@ int hpsht_plan_destroy(hpsht_plan* plan) {
     cudaSetDevice(plan->device);
     if (plan->stream) cudaStreamSynchronize(plan->stream);
     if (plan->comm) NcclApi::get().CommDestroy(plan->comm);
+    if (plan->cstream) cudaStreamSynchronize(plan->cstream);
+    for (auto& e : plan->ev_slab) cudaEventDestroy(e);
+    for (auto& e : plan->ev_done) cudaEventDestroy(e);
+    for (auto& st : plan->sstream) {
+      cudaStreamSynchronize(st);
+      cudaStreamDestroy(st);
+    }
+    if (plan->ev_ready) cudaEventDestroy(plan->ev_ready);
+    if (plan->cstream) cudaStreamDestroy(plan->cstream);
     if (plan->stream) cudaStreamDestroy(plan->stream);
     delete plan;
   });

@@ -169,16 +169,36 @@ struct LegParams {
   const double* sh;
   const double* ch;
   const int* mlim;
-  const int64_t* offN;
-  const int64_t* offS;
-  const int64_t* mstr;
-  const int64_t* cstr;
+  // leg addressing: element (pair p, local m index mi, component c) of ring "N" lives at
+  //   a0[p] + nrr[p] * (ncs * sstart[mi] + c * nms[mi]) + jN[p] * nms[mi] + (mi - sstart[mi])
+  // i.e. per destination block [m-slab][component][ring][m within slab]; a single slab with
+  // sstart = 0, nms = nm is the reference's (nm, nring, ncomp) array.
+  const int64_t* a0;
+  const int64_t* nrr;
+  const int64_t* jN;
+  const int64_t* jS;      // -1: unpaired
+  const int64_t* sstart;  // per local m
+  const int64_t* nms;     // per local m
+  int64_t ncs;            // components the slab blocks are sized for
   // data
   const double* stream;   // 4 doubles / step (synthesis input)
   double* leg;            // complex128 (synthesis out / adjoint in)
   double* part;           // adjoint partial sums, 4 doubles / step
   const int64_t* partoff; // per item: offset in steps into part
 };
+
+__device__ __forceinline__ int64_t leg_rowoff(const LegParams& P, int p, int mi) {
+  const int64_t ss = P.sstart[mi];
+  return P.nrr[p] * (P.ncs * ss) + ((int64_t)mi - ss);
+}
+__device__ __forceinline__ int64_t leg_offN(const LegParams& P, int p, int mi) {
+  return P.a0[p] + P.jN[p] * P.nms[mi];
+}
+__device__ __forceinline__ int64_t leg_offS(const LegParams& P, int p, int mi) {
+  const int64_t j = P.jS[p];
+  return j < 0 ? -1 : P.a0[p] + j * P.nms[mi];
+}
+__device__ __forceinline__ int64_t leg_cstr(const LegParams& P, int p, int mi) { return P.nrr[p] * P.nms[mi]; }
 
 // ------------------------------------------------------------------------------------------------
 // producer side of the coefficient pipeline.  One thread issues the 1-D TMA bulk copies of chunk
@@ -376,9 +396,9 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
     const double c = P.cth[p];
     const double Er = on ? er[r] : 0.0, Ei = on ? ei[r] : 0.0;
     const double Or = on ? orr[r] * c : 0.0, Oi = on ? oi[r] * c : 0.0;
-    const int64_t rowoff = (int64_t)mi * P.mstr[p];
-    leg[P.offN[p] + rowoff] = make_double2(Er + Or, Ei + Oi);
-    const int64_t oS = P.offS[p];
+    const int64_t rowoff = leg_rowoff(P, p, mi);
+    leg[leg_offN(P, p, mi) + rowoff] = make_double2(Er + Or, Ei + Oi);
+    const int64_t oS = leg_offS(P, p, mi);
     if (oS >= 0) leg[oS + rowoff] = make_double2(Er - Or, Ei - Oi);
   }
 }
@@ -565,13 +585,13 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
     const double MSr = onp ? msr[r] * sgnS : 0.0, MSi = onp ? msi[r] * sgnS : 0.0;
     const double MNr = onm ? mnr[r] : 0.0, MNi = onm ? mni[r] : 0.0;
     const double PSr = onm ? psr[r] * sgnS : 0.0, PSi = onm ? psi[r] * sgnS : 0.0;
-    const int64_t rowoff = (int64_t)mi * P.mstr[p];
-    const int64_t cs = P.cstr[p];
-    const int64_t oN = P.offN[p] + rowoff;
+    const int64_t rowoff = leg_rowoff(P, p, mi);
+    const int64_t cs = leg_cstr(P, p, mi);
+    const int64_t oN = leg_offN(P, p, mi) + rowoff;
     // Q = P+ + P- ; U = -i (P+ - P-) = ( Im(P+ - P-), -Re(P+ - P-) )
     leg[oN] = make_double2(PNr + MNr, PNi + MNi);
     leg[oN + cs] = make_double2(PNi - MNi, -(PNr - MNr));
-    const int64_t oS0 = P.offS[p];
+    const int64_t oS0 = leg_offS(P, p, mi);
     if (oS0 >= 0) {
       const int64_t oS = oS0 + rowoff;
       leg[oS] = make_double2(PSr + MSr, PSi + MSi);
@@ -667,9 +687,9 @@ __global__ void __launch_bounds__((NW + (PROD == 1 ? 1 : 0)) * 32, 2) k_leg2alm_
     bool any_act = false;
 
     auto load_in = [&](int r, int p) {
-      const int64_t rowoff = (int64_t)mi * P.mstr[p];
-      const double2 gN = leg[P.offN[p] + rowoff];
-      const int64_t oS = P.offS[p];
+      const int64_t rowoff = leg_rowoff(P, p, mi);
+      const double2 gN = leg[leg_offN(P, p, mi) + rowoff];
+      const int64_t oS = leg_offS(P, p, mi);
       const double2 gS = oS >= 0 ? leg[oS + rowoff] : make_double2(0.0, 0.0);
       const double cc = P.cth[p];
       er[r] = gN.x + gS.x;
@@ -842,13 +862,13 @@ __global__ void __launch_bounds__((NW + (PROD == 1 ? 1 : 0)) * 32, 2) k_leg2alm_
     bool any_act = false;
 
     auto load_p = [&](int r, int p) {  // inputs multiplied by d+
-      const int64_t rowoff = (int64_t)mi * P.mstr[p];
-      const int64_t cs = P.cstr[p];
-      const double2 qN = leg[P.offN[p] + rowoff], uN = leg[P.offN[p] + rowoff + cs];
+      const int64_t rowoff = leg_rowoff(P, p, mi);
+      const int64_t cs = leg_cstr(P, p, mi);
+      const double2 qN = leg[leg_offN(P, p, mi) + rowoff], uN = leg[leg_offN(P, p, mi) + rowoff + cs];
       // w+N = Q + iU = (qr - ui, qi + ur)
       wpNr[r] = qN.x - uN.y;
       wpNi[r] = qN.y + uN.x;
-      const int64_t oS = P.offS[p];
+      const int64_t oS = leg_offS(P, p, mi);
       if (oS >= 0) {
         const double2 qS = leg[oS + rowoff], uS = leg[oS + rowoff + cs];
         // w-S = Q - iU = (qr + ui, qi - ur)
@@ -859,12 +879,12 @@ __global__ void __launch_bounds__((NW + (PROD == 1 ? 1 : 0)) * 32, 2) k_leg2alm_
       }
     };
     auto load_m = [&](int r, int p) {  // inputs multiplied by d-
-      const int64_t rowoff = (int64_t)mi * P.mstr[p];
-      const int64_t cs = P.cstr[p];
-      const double2 qN = leg[P.offN[p] + rowoff], uN = leg[P.offN[p] + rowoff + cs];
+      const int64_t rowoff = leg_rowoff(P, p, mi);
+      const int64_t cs = leg_cstr(P, p, mi);
+      const double2 qN = leg[leg_offN(P, p, mi) + rowoff], uN = leg[leg_offN(P, p, mi) + rowoff + cs];
       wmNr[r] = qN.x + uN.y;
       wmNi[r] = qN.y - uN.x;
-      const int64_t oS = P.offS[p];
+      const int64_t oS = leg_offS(P, p, mi);
       if (oS >= 0) {
         const double2 qS = leg[oS + rowoff], uS = leg[oS + rowoff + cs];
         wpSr[r] = sgnS * (qS.x - uS.y);
@@ -1105,9 +1125,9 @@ __global__ void __launch_bounds__(32) k_leg2alm_s0_w(LegParams P) {
     bool any_act = false;
 
     auto load_in = [&](int r, int p) {
-      const int64_t rowoff = (int64_t)mi * P.mstr[p];
-      const double2 gN = leg[P.offN[p] + rowoff];
-      const int64_t oS = P.offS[p];
+      const int64_t rowoff = leg_rowoff(P, p, mi);
+      const double2 gN = leg[leg_offN(P, p, mi) + rowoff];
+      const int64_t oS = leg_offS(P, p, mi);
       const double2 gS = oS >= 0 ? leg[oS + rowoff] : make_double2(0.0, 0.0);
       const double cc = P.cth[p];
       er[r] = gN.x + gS.x;
@@ -1280,12 +1300,12 @@ __global__ void __launch_bounds__(32) k_leg2alm_s2_w(LegParams P) {
     bool any_act = false;
 
     auto load_p = [&](int r, int p) {  // inputs multiplied by d+
-      const int64_t rowoff = (int64_t)mi * P.mstr[p];
-      const int64_t cs = P.cstr[p];
-      const double2 qN = leg[P.offN[p] + rowoff], uN = leg[P.offN[p] + rowoff + cs];
+      const int64_t rowoff = leg_rowoff(P, p, mi);
+      const int64_t cs = leg_cstr(P, p, mi);
+      const double2 qN = leg[leg_offN(P, p, mi) + rowoff], uN = leg[leg_offN(P, p, mi) + rowoff + cs];
       wpNr[r] = qN.x - uN.y;
       wpNi[r] = qN.y + uN.x;
-      const int64_t oS = P.offS[p];
+      const int64_t oS = leg_offS(P, p, mi);
       if (oS >= 0) {
         const double2 qS = leg[oS + rowoff], uS = leg[oS + rowoff + cs];
         wmSr[r] = sgnS * (qS.x + uS.y);
@@ -1295,12 +1315,12 @@ __global__ void __launch_bounds__(32) k_leg2alm_s2_w(LegParams P) {
       }
     };
     auto load_m = [&](int r, int p) {  // inputs multiplied by d-
-      const int64_t rowoff = (int64_t)mi * P.mstr[p];
-      const int64_t cs = P.cstr[p];
-      const double2 qN = leg[P.offN[p] + rowoff], uN = leg[P.offN[p] + rowoff + cs];
+      const int64_t rowoff = leg_rowoff(P, p, mi);
+      const int64_t cs = leg_cstr(P, p, mi);
+      const double2 qN = leg[leg_offN(P, p, mi) + rowoff], uN = leg[leg_offN(P, p, mi) + rowoff + cs];
       wmNr[r] = qN.x + uN.y;
       wmNi[r] = qN.y - uN.x;
-      const int64_t oS = P.offS[p];
+      const int64_t oS = leg_offS(P, p, mi);
       if (oS >= 0) {
         const double2 qS = leg[oS + rowoff], uS = leg[oS + rowoff + cs];
         wpSr[r] = sgnS * (qS.x - uS.y);
@@ -1634,7 +1654,7 @@ namespace {
 // kernel configurations
 // synthesis kernel variants (R pairs per thread, NW consumer warps); selectable at run time for tuning
 struct SynCfg { int R, NW; };
-static const SynCfg kSynCfgs[] = {{2, 4}, {4, 4}, {2, 8}, {3, 4}, {4, 2}, {4, 1}, {8, 1}, {2, 1}, {3, 1}, {2, 2}};
+static const SynCfg kSynCfgs[] = {{2, 4}, {4, 4}, {2, 8}, {3, 4}, {4, 2}, {4, 1}, {8, 1}, {2, 1}, {3, 1}, {2, 2}, {6, 4}, {8, 4}, {8, 2}};
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -1656,7 +1676,10 @@ static int env_adj_prod() { return env_int("HPSHT_ADJ_PROD", 2); }
       case 6: KERNEL<8, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
       case 7: KERNEL<2, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
       case 8: KERNEL<3, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
-      default: KERNEL<2, 2, PROD><<<(unsigned)(nitems), 2 * 32 + xw, 0, stream>>>(P); break;           \
+      case 9: KERNEL<2, 2, PROD><<<(unsigned)(nitems), 2 * 32 + xw, 0, stream>>>(P); break;            \
+      case 10: KERNEL<6, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;           \
+      case 11: KERNEL<8, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;           \
+      default: KERNEL<8, 2, PROD><<<(unsigned)(nitems), 2 * 32 + xw, 0, stream>>>(P); break;           \
     }                                                                                                  \
   } while (0)
 #define HP_LAUNCH(KERNEL, prod, cfgidx, nitems, stream, P)                                            \
@@ -1750,33 +1773,47 @@ void LegendreStage::setup(int64_t lmax, const int64_t* mval, const int64_t* msta
   mval_.assign(mval, mval + nm);
   mstart_.assign(mstart, mstart + nm);
   layout_ = layout;
-  HP_REQUIRE((int64_t)layout.base.size() == nring, HPSHT_ERR_INTERNAL, "layout size mismatch");
+  HP_REQUIRE((int64_t)layout.a0.size() == nring && (int64_t)layout.nr.size() == nring &&
+                 (int64_t)layout.j.size() == nring,
+             HPSHT_ERR_INTERNAL, "layout size mismatch");
+  // m-slabs: default = one slab holding every local m (the reference's (nm, nring, ncomp) array)
+  if (layout_.sstart.empty()) {
+    layout_.sstart.assign((size_t)nm, 0);
+    layout_.nms.assign((size_t)nm, nm);
+    layout_.ncs = max_ncomp;
+  }
+  HP_REQUIRE((int64_t)layout_.sstart.size() == nm && (int64_t)layout_.nms.size() == nm, HPSHT_ERR_INTERNAL,
+             "slab table size mismatch");
+  slab_first_mi_.clear();
+  for (int64_t i = 0; i < nm; ++i)
+    if (i == 0 || layout_.sstart[(size_t)i] != layout_.sstart[(size_t)i - 1]) slab_first_mi_.push_back((int)i);
+  slab_first_mi_.push_back((int)nm);
   pairs_ = build_pairs(lmax, nring, theta);
   npairs_ = (int64_t)pairs_.size();
   HP_REQUIRE(npairs_ < (1ll << 30) && nm < (1ll << 30), HPSHT_ERR_UNSUPPORTED, "problem too large");
 
-  std::vector<double> cth((size_t)npairs_), sth((size_t)npairs_), sh((size_t)npairs_), ch((size_t)npairs_);
-  std::vector<int> ml0((size_t)npairs_), ml2((size_t)npairs_);
-  std::vector<int64_t> offN((size_t)npairs_), offS((size_t)npairs_), mstr((size_t)npairs_), cstr((size_t)npairs_);
+  const size_t np = (size_t)npairs_;
+  std::vector<double> cth(np), sth(np), sh(np), ch(np);
+  std::vector<int> ml0(np), ml2(np);
+  std::vector<int64_t> a0(np), nrr(np), jN(np), jS(np);
   culled0_ = culled2_ = dense_ = 0;
-  for (int64_t p = 0; p < npairs_; ++p) {
-    const PairHost& q = pairs_[(size_t)p];
-    cth[(size_t)p] = q.cth;
-    sth[(size_t)p] = q.sth;
-    sh[(size_t)p] = q.sh;
-    ch[(size_t)p] = q.ch;
-    ml0[(size_t)p] = q.mlim0;
-    ml2[(size_t)p] = q.mlim2;
-    offN[(size_t)p] = layout.base[(size_t)q.slotN];
-    mstr[(size_t)p] = layout.mstride[(size_t)q.slotN];
-    cstr[(size_t)p] = layout.cstride[(size_t)q.slotN];
+  for (size_t p = 0; p < np; ++p) {
+    const PairHost& q = pairs_[p];
+    cth[p] = q.cth;
+    sth[p] = q.sth;
+    sh[p] = q.sh;
+    ch[p] = q.ch;
+    ml0[p] = q.mlim0;
+    ml2[p] = q.mlim2;
+    a0[p] = layout.a0[(size_t)q.slotN];
+    nrr[p] = layout.nr[(size_t)q.slotN];
+    jN[p] = layout.j[(size_t)q.slotN];
     if (q.slotS >= 0) {
-      offS[(size_t)p] = layout.base[(size_t)q.slotS];
-      HP_REQUIRE(layout.mstride[(size_t)q.slotS] == mstr[(size_t)p] &&
-                     layout.cstride[(size_t)q.slotS] == cstr[(size_t)p],
-                 HPSHT_ERR_INTERNAL, "N/S rings of a pair must share strides");
+      HP_REQUIRE(layout.a0[(size_t)q.slotS] == a0[p] && layout.nr[(size_t)q.slotS] == nrr[p],
+                 HPSHT_ERR_INTERNAL, "N/S rings of a pair must live in the same block");
+      jS[p] = layout.j[(size_t)q.slotS];
     } else {
-      offS[(size_t)p] = -1;
+      jS[p] = -1;
     }
     for (int64_t i = 0; i < nm; ++i) {
       const double w = (double)(lmax - mval[i] + 1);
@@ -1786,22 +1823,36 @@ void LegendreStage::setup(int64_t lmax, const int64_t* mval, const int64_t* msta
       if (mval[i] <= q.mlim2) culled2_ += w;
     }
   }
-  d_cth_.upload(cth.data(), cth.size(), stream);
-  d_sth_.upload(sth.data(), sth.size(), stream);
-  d_sh_.upload(sh.data(), sh.size(), stream);
-  d_ch_.upload(ch.data(), ch.size(), stream);
-  d_mlim0_.upload(ml0.data(), ml0.size(), stream);
-  d_mlim2_.upload(ml2.data(), ml2.size(), stream);
-  d_offN_.upload(offN.data(), offN.size(), stream);
-  d_offS_.upload(offS.data(), offS.size(), stream);
-  d_mstr_.upload(mstr.data(), mstr.size(), stream);
-  d_cstr_.upload(cstr.data(), cstr.size(), stream);
+  d_cth_.upload(cth.data(), np, stream);
+  d_sth_.upload(sth.data(), np, stream);
+  d_sh_.upload(sh.data(), np, stream);
+  d_ch_.upload(ch.data(), np, stream);
+  d_mlim0_.upload(ml0.data(), np, stream);
+  d_mlim2_.upload(ml2.data(), np, stream);
+  d_a0_.upload(a0.data(), np, stream);
+  d_nrr_.upload(nrr.data(), np, stream);
+  d_jN_.upload(jN.data(), np, stream);
+  d_jS_.upload(jS.data(), np, stream);
+  d_sstart_.upload(layout_.sstart.data(), (size_t)nm, stream);
+  d_nms_.upload(layout_.nms.data(), (size_t)nm, stream);
   d_mval_.upload(mval_.data(), mval_.size(), stream);
   d_mstart_.upload(mstart_.data(), mstart_.size(), stream);
   HP_CUDA(cudaStreamSynchronize(stream));
   if (!ev0_) HP_CUDA(cudaEventCreate(&ev0_));
   if (!ev1_) HP_CUDA(cudaEventCreate(&ev1_));
   have0_ = have2_ = false;
+}
+
+// first item of every m-slab (items are ordered by local m index)
+static std::vector<int> slab_item_ranges(const std::vector<WorkItem>& items, const std::vector<int>& slab_first_mi) {
+  std::vector<int> r(slab_first_mi.size(), (int)items.size());
+  size_t it = 0;
+  for (size_t s = 0; s + 1 < slab_first_mi.size(); ++s) {
+    while (it < items.size() && items[it].mi < slab_first_mi[s]) ++it;
+    r[s] = (int)it;
+  }
+  r.back() = (int)items.size();
+  return r;
 }
 
 void LegendreStage::ensure_spin(int spin, cudaStream_t stream) {
@@ -1834,6 +1885,8 @@ void LegendreStage::ensure_spin(int spin, cudaStream_t stream) {
     d_apartoff0_.upload(apartoff0_.data(), apartoff0_.size(), stream);
     nstep0_h_ = T.nstep0;
     off0_h_ = T.off0;
+    srange_s0_ = slab_item_ranges(items_s0_, slab_first_mi_);
+    srange_a0_ = slab_item_ranges(items_a0_, slab_first_mi_);
     have0_ = true;
   } else {
     d_nstep2_.upload(T.nstep2.data(), T.nstep2.size(), stream);
@@ -1858,6 +1911,8 @@ void LegendreStage::ensure_spin(int spin, cudaStream_t stream) {
     d_apartoff2_.upload(apartoff2_.data(), apartoff2_.size(), stream);
     nstep2_h_ = T.nstep2;
     off2_h_ = T.off2;
+    srange_s2_ = slab_item_ranges(items_s2_, slab_first_mi_);
+    srange_a2_ = slab_item_ranges(items_a2_, slab_first_mi_);
     have2_ = true;
   }
   part_steps_need_ = std::max(part_steps_need_, part_steps);
@@ -1872,24 +1927,50 @@ static inline int64_t max_of(const std::vector<int64_t>& v) {
   return m;
 }
 
-void LegendreStage::alm2leg(const double* d_alm, int64_t alm_cstride, double* d_leg,
-                            int64_t leg_elems, int ncomp, cudaStream_t stream) {
-  const int spin = ncomp == 1 ? 0 : 2;
-  ensure_spin(spin, stream);
-  // (m, ring) combinations beyond mlim are never visited by a CTA: their leg is exactly 0
-  HP_CUDA(cudaMemsetAsync(d_leg, 0, (size_t)leg_elems * 2 * sizeof(double), stream));
-  LegParams P;
+void LegendreStage::fill_params(LegParams& P, int spin, bool adjoint) const {
   std::memset(&P, 0, sizeof(P));
   P.mval = d_mval_.p;
   P.cth = d_cth_.p;
   P.sth = d_sth_.p;
   P.sh = d_sh_.p;
   P.ch = d_ch_.p;
-  P.offN = d_offN_.p;
-  P.offS = d_offS_.p;
-  P.mstr = d_mstr_.p;
-  P.cstr = d_cstr_.p;
-  P.leg = d_leg;
+  P.a0 = d_a0_.p;
+  P.nrr = d_nrr_.p;
+  P.jN = d_jN_.p;
+  P.jS = d_jS_.p;
+  P.sstart = d_sstart_.p;
+  P.nms = d_nms_.p;
+  P.ncs = layout_.ncs;
+  if (spin == 0) {
+    P.items = adjoint ? d_items_a0_.p : d_items_s0_.p;
+    P.nstep = d_nstep0_.p;
+    P.off = d_off0_.p;
+    P.coef = d_coef0_.p;
+    P.k0 = d_k0_.p;
+    P.mlim = d_mlim0_.p;
+    P.stream = d_stream0_.p;
+    P.partoff = d_apartoff0_.p;
+  } else {
+    P.items = adjoint ? d_items_a2_.p : d_items_s2_.p;
+    P.nstep = d_nstep2_.p;
+    P.off = d_off2_.p;
+    P.coef = d_coef2_.p;
+    P.k0 = d_kp2_.p;
+    P.k1 = d_km2_.p;
+    P.mlim = d_mlim2_.p;
+    P.stream = d_stream2_.p;
+    P.partoff = d_apartoff2_.p;
+  }
+  P.part = d_part_.p;
+}
+
+// ---- synthesis ------------------------------------------------------------------------------
+void LegendreStage::alm2leg_begin(const double* d_alm, int64_t alm_cstride, double* d_leg,
+                                  int64_t leg_elems, int ncomp, cudaStream_t stream) {
+  const int spin = ncomp == 1 ? 0 : 2;
+  ensure_spin(spin, stream);
+  // (m, ring) combinations beyond mlim are never visited by a CTA: their leg is exactly 0
+  HP_CUDA(cudaMemsetAsync(d_leg, 0, (size_t)leg_elems * 2 * sizeof(double), stream));
   const int TB = 256;
   if (spin == 0) {
     const int64_t mx = max_of(nstep0_h_);
@@ -1898,19 +1979,6 @@ void LegendreStage::alm2leg(const double* d_alm, int64_t alm_cstride, double* d_
       k_prep_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(d_alm), d_mval_.p,
                                          d_mstart_.p, d_nstep0_.p, d_off0_.p, d_invs0_.p, lmax_,
                                          reinterpret_cast<Strm*>(d_stream0_.p));
-      ++launches_;
-    }
-    P.items = d_items_s0_.p;
-    P.nstep = d_nstep0_.p;
-    P.off = d_off0_.p;
-    P.coef = d_coef0_.p;
-    P.k0 = d_k0_.p;
-    P.mlim = d_mlim0_.p;
-    P.stream = d_stream0_.p;
-    if (!items_s0_.empty()) {
-      cudaEventRecord(ev0_, stream);
-      HP_LAUNCH(k_alm2leg_s0, env_syn_prod(), s0_cfg(), items_s0_.size(), stream, P);
-      cudaEventRecord(ev1_, stream);
       ++launches_;
     }
   } else {
@@ -1923,68 +1991,78 @@ void LegendreStage::alm2leg(const double* d_alm, int64_t alm_cstride, double* d_
                                          reinterpret_cast<Strm*>(d_stream2_.p));
       ++launches_;
     }
-    P.items = d_items_s2_.p;
-    P.nstep = d_nstep2_.p;
-    P.off = d_off2_.p;
-    P.coef = d_coef2_.p;
-    P.k0 = d_kp2_.p;
-    P.k1 = d_km2_.p;
-    P.mlim = d_mlim2_.p;
-    P.stream = d_stream2_.p;
-    if (!items_s2_.empty()) {
-      cudaEventRecord(ev0_, stream);
-      HP_LAUNCH(k_alm2leg_s2, env_syn_prod(), s2_cfg(), items_s2_.size(), stream, P);
-      cudaEventRecord(ev1_, stream);
-      ++launches_;
-    }
   }
   HP_CUDA(cudaGetLastError());
+  cudaEventRecord(ev0_, stream);
 }
 
-void LegendreStage::leg2alm(const double* d_leg, double* d_alm, int64_t alm_cstride, int ncomp,
-                            cudaStream_t stream) {
+void LegendreStage::alm2leg_slab(int slab, double* d_leg, int ncomp, cudaStream_t stream) {
+  const int spin = ncomp == 1 ? 0 : 2;
+  const std::vector<int>& sr = spin == 0 ? srange_s0_ : srange_s2_;
+  const int first = sr[(size_t)slab], count = sr[(size_t)slab + 1] - first;
+  if (count > 0) {
+    LegParams P;
+    fill_params(P, spin, false);
+    P.items += first;
+    P.leg = d_leg;
+    if (spin == 0)
+      HP_LAUNCH(k_alm2leg_s0, env_syn_prod(), s0_cfg(), count, stream, P);
+    else
+      HP_LAUNCH(k_alm2leg_s2, env_syn_prod(), s2_cfg(), count, stream, P);
+    ++launches_;
+    HP_CUDA(cudaGetLastError());
+  }
+  if (slab == nslabs() - 1) cudaEventRecord(ev1_, stream);
+}
+
+void LegendreStage::alm2leg(const double* d_alm, int64_t alm_cstride, double* d_leg,
+                            int64_t leg_elems, int ncomp, cudaStream_t stream) {
+  alm2leg_begin(d_alm, alm_cstride, d_leg, leg_elems, ncomp, stream);
+  for (int s = 0; s < nslabs(); ++s) alm2leg_slab(s, d_leg, ncomp, stream);
+}
+
+// ---- adjoint --------------------------------------------------------------------------------
+void LegendreStage::leg2alm_begin(int ncomp, cudaStream_t stream) {
   const int spin = ncomp == 1 ? 0 : 2;
   ensure_spin(spin, stream);
   d_part_.ensure(part_steps_need_ * 4);
   d_accum_.ensure(accum_steps_need_ * 4);
-  LegParams P;
-  std::memset(&P, 0, sizeof(P));
-  P.mval = d_mval_.p;
-  P.cth = d_cth_.p;
-  P.sth = d_sth_.p;
-  P.sh = d_sh_.p;
-  P.ch = d_ch_.p;
-  P.offN = d_offN_.p;
-  P.offS = d_offS_.p;
-  P.mstr = d_mstr_.p;
-  P.cstr = d_cstr_.p;
-  P.leg = const_cast<double*>(d_leg);
-  P.part = d_part_.p;
+  cudaEventRecord(ev0_, stream);
+}
+
+void LegendreStage::leg2alm_slab(int slab, const double* d_leg, int ncomp, cudaStream_t stream) {
+  const int spin = ncomp == 1 ? 0 : 2;
+  const std::vector<int>& sr = spin == 0 ? srange_a0_ : srange_a2_;
+  const int first = sr[(size_t)slab], count = sr[(size_t)slab + 1] - first;
+  if (count > 0) {
+    LegParams P;
+    fill_params(P, spin, true);
+    P.items += first;
+    P.partoff += first;
+    P.leg = const_cast<double*>(d_leg);
+    if (spin == 0) {
+      if (adj_warp_mode())
+        HP_LAUNCH_W(k_leg2alm_s0_w, a0w_R(), count, stream, P);
+      else
+        HP_LAUNCH(k_leg2alm_s0, env_adj_prod(), a0_cfg(), count, stream, P);
+    } else {
+      if (adj_warp_mode())
+        HP_LAUNCH_W(k_leg2alm_s2_w, a2w_R(), count, stream, P);
+      else
+        HP_LAUNCH(k_leg2alm_s2, env_adj_prod(), a2_cfg(), count, stream, P);
+    }
+    ++launches_;
+    HP_CUDA(cudaGetLastError());
+  }
+  if (slab == nslabs() - 1) cudaEventRecord(ev1_, stream);
+}
+
+void LegendreStage::mark_main_end(cudaStream_t stream) { cudaEventRecord(ev1_, stream); }
+
+void LegendreStage::leg2alm_end(double* d_alm, int64_t alm_cstride, int ncomp, cudaStream_t stream) {
+  const int spin = ncomp == 1 ? 0 : 2;
   const int TB = 256;
   if (spin == 0) {
-    P.items = d_items_a0_.p;
-    P.nstep = d_nstep0_.p;
-    P.off = d_off0_.p;
-    P.coef = d_coef0_.p;
-    P.k0 = d_k0_.p;
-    P.mlim = d_mlim0_.p;
-    P.partoff = d_apartoff0_.p;
-    if (!items_a0_.empty()) {
-      cudaEventRecord(ev0_, stream);
-      if (adj_warp_mode())
-        if (env_int("HPSHT_DBG", 0) == 1) {
-          if (a0w_R() == 4) k_leg2alm_s0_w<4, 1><<<(unsigned)items_a0_.size(), 32, 0, stream>>>(P);
-          else k_leg2alm_s0_w<8, 1><<<(unsigned)items_a0_.size(), 32, 0, stream>>>(P);
-        } else if (env_int("HPSHT_DBG", 0) == 2) {
-          if (a0w_R() == 4) k_leg2alm_s0_w<4, 2><<<(unsigned)items_a0_.size(), 32, 0, stream>>>(P);
-          else k_leg2alm_s0_w<8, 2><<<(unsigned)items_a0_.size(), 32, 0, stream>>>(P);
-        } else
-          HP_LAUNCH_W(k_leg2alm_s0_w, a0w_R(), items_a0_.size(), stream, P);
-      else
-        HP_LAUNCH(k_leg2alm_s0, env_adj_prod(), a0_cfg(), items_a0_.size(), stream, P);
-      cudaEventRecord(ev1_, stream);
-      ++launches_;
-    }
     const int64_t mx = max_of(nstep0_h_);
     if (mx > 0) {
       dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
@@ -1998,23 +2076,6 @@ void LegendreStage::leg2alm(const double* d_leg, double* d_alm, int64_t alm_cstr
       launches_ += 2;
     }
   } else {
-    P.items = d_items_a2_.p;
-    P.nstep = d_nstep2_.p;
-    P.off = d_off2_.p;
-    P.coef = d_coef2_.p;
-    P.k0 = d_kp2_.p;
-    P.k1 = d_km2_.p;
-    P.mlim = d_mlim2_.p;
-    P.partoff = d_apartoff2_.p;
-    if (!items_a2_.empty()) {
-      cudaEventRecord(ev0_, stream);
-      if (adj_warp_mode())
-        HP_LAUNCH_W(k_leg2alm_s2_w, a2w_R(), items_a2_.size(), stream, P);
-      else
-        HP_LAUNCH(k_leg2alm_s2, env_adj_prod(), a2_cfg(), items_a2_.size(), stream, P);
-      cudaEventRecord(ev1_, stream);
-      ++launches_;
-    }
     int64_t mx = max_of(nstep2_h_);
     mx = std::max<int64_t>(mx, 1);  // the post kernel also zeroes l < 2
     dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
@@ -2028,6 +2089,13 @@ void LegendreStage::leg2alm(const double* d_leg, double* d_alm, int64_t alm_cstr
     launches_ += 2;
   }
   HP_CUDA(cudaGetLastError());
+}
+
+void LegendreStage::leg2alm(const double* d_leg, double* d_alm, int64_t alm_cstride, int ncomp,
+                            cudaStream_t stream) {
+  leg2alm_begin(ncomp, stream);
+  for (int s = 0; s < nslabs(); ++s) leg2alm_slab(s, d_leg, ncomp, stream);
+  leg2alm_end(d_alm, alm_cstride, ncomp, stream);
 }
 
 }  // namespace hpsht

@@ -24,10 +24,17 @@ struct PairHost {
   int mlim0, mlim2;          // m > mlim  => culled
 };
 
-// Where ring slot `slot` of local-m row `mi`, component `comp` lives in the leg buffer (in complex
-// elements):  base[slot] + mi*mstride[slot] + comp*cstride[slot].
+// Leg addressing.  Ring slot `slot` belongs to a block starting at a0[slot] that holds nr[slot] rings,
+// the slot being ring j[slot] of that block; local m's are grouped in contiguous slabs
+// (sstart[mi] = first local m index of mi's slab, nms[mi] = number of m in it).  Element
+// (slot, mi, comp) lives at
+//     a0 + nr * (ncs * sstart + comp * nms) + j * nms + (mi - sstart)          [complex elements]
+// i.e. block layout [m-slab][component][ring][m within slab].  With one slab (sstart = 0, nms = nm) and
+// a0 = 0, nr = nring, j = slot this is the reference's (nm, nring, ncomp) column-major array.
 struct LegLayout {
-  std::vector<int64_t> base, mstride, cstride;  // per ring slot
+  std::vector<int64_t> a0, nr, j;      // per ring slot
+  std::vector<int64_t> sstart, nms;    // per local m (empty: single slab)
+  int64_t ncs = 1;                     // components the slab blocks are sized for
 };
 
 struct WorkItem {
@@ -56,6 +63,17 @@ class LegendreStage {
   // leg -> alm
   void leg2alm(const double* d_leg, double* d_alm, int64_t alm_cstride, int ncomp,
                cudaStream_t stream);
+  // the same, slab by slab (lets the caller overlap the leg exchange of one m-slab with the
+  // Legendre work of the next): begin, then every slab 0..nslabs()-1 in order, then (adjoint) end
+  int nslabs() const { return (int)slab_first_mi_.size() - 1; }
+  void alm2leg_begin(const double* d_alm, int64_t alm_cstride, double* d_leg, int64_t leg_elems,
+                     int ncomp, cudaStream_t stream);
+  void alm2leg_slab(int slab, double* d_leg, int ncomp, cudaStream_t stream);
+  void leg2alm_begin(int ncomp, cudaStream_t stream);
+  void leg2alm_slab(int slab, const double* d_leg, int ncomp, cudaStream_t stream);
+  void leg2alm_end(double* d_alm, int64_t alm_cstride, int ncomp, cudaStream_t stream);
+  // re-records the end-of-main-kernel timing event (when slab kernels ran on other streams)
+  void mark_main_end(cudaStream_t stream);
 
   double steps_culled(int spin) const { return spin ? culled2_ : culled0_; }
   double steps_dense() const { return dense_; }
@@ -67,6 +85,9 @@ class LegendreStage {
 
  private:
   void ensure_spin(int spin, cudaStream_t stream);
+  void fill_params(struct LegParams& P, int spin, bool adjoint) const;
+  std::vector<int> slab_first_mi_;
+  std::vector<int> srange_s0_, srange_s2_, srange_a0_, srange_a2_;  // first item of each slab
 
   int64_t lmax_ = 0, nm_ = 0, nring_ = 0, npairs_ = 0;
   int max_ncomp_ = 1;
@@ -82,7 +103,7 @@ class LegendreStage {
   // device: geometry
   DevBuf<double> d_cth_, d_sth_, d_sh_, d_ch_;
   DevBuf<int> d_mlim0_, d_mlim2_;
-  DevBuf<int64_t> d_offN_, d_offS_, d_mstr_, d_cstr_;
+  DevBuf<int64_t> d_a0_, d_nrr_, d_jN_, d_jS_, d_sstart_, d_nms_;
   DevBuf<int64_t> d_mval_, d_mstart_;
   // device: tables
   DevBuf<int64_t> d_off0_, d_off2_, d_nstep0_, d_nstep2_;
