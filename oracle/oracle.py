@@ -48,6 +48,12 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def set_reference_cut(on: bool) -> None:
+    """Apply (or not) the libsharp/ducc m > mlim(theta) ring-culling rule inside alm2leg / leg2alm, to
+    separate an implementation's arithmetic error from the cut the reference's backend makes."""
+    lib().orc_set_cut(C.c_int(1 if on else 0))
+
+
 def _i64(a):
     return np.ascontiguousarray(a, dtype=i64)
 

@@ -249,6 +249,30 @@ void orc_lambda(int s, int64_t lmax, int64_t m, double theta, ld* out) {
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Optional: the ring-culling rule of libsharp / ducc0 [UPSTREAM, published algorithm; SURVEY 8d]:
+ * (m, ring) combinations with m > mlim(theta) are skipped by the reference's backend (their leg is
+ * exactly 0 / they do not contribute to a_lm).  With white-noise a_lm at lmax = 8191 the skipped
+ * terms are ~1e-11 of a ring's norm, i.e. larger than the 1e-12 parity target, so "the exact sum"
+ * and "what the reference computes" differ by that much.  orc_set_cut(1) makes the oracle apply the
+ * same rule so that the arithmetic error of an implementation can be separated from the cut.
+ * ---------------------------------------------------------------------------------------- */
+static int g_apply_cut = 0;
+void orc_set_cut(int on) { g_apply_cut = on; }
+int64_t orc_mlim(int64_t lmax, int spin, double theta) {
+  double sth = (double)sinl((ld)theta), cth = (double)cosl((ld)theta);
+  double ofs = lmax * 0.01;
+  if (ofs < 100.) ofs = 100.;
+  double b = -2. * spin * fabs(cth);
+  double t1 = lmax * sth + ofs;
+  double c = (double)spin * spin - t1 * t1;
+  double discr = b * b - 4. * c;
+  if (discr <= 0) return lmax;
+  double res = (-b + sqrt(discr)) / 2.;
+  if (res > lmax) res = (double)lmax;
+  return (int64_t)(res + 0.5);
+}
+
+/* ------------------------------------------------------------------------------------------
  * alm2leg  (what Ducc0.Sht.alm2leg! computes at src/sht.jl:85)
  *   alm : double complex, alm[comp*alm_cstride + mstart[mi] + l]   (mstart 0-based)
  *   leg : long double complex (re,im interleaved), leg[((comp*nring + ir)*nm + mi)]
@@ -270,6 +294,14 @@ void orc_alm2leg(int spin, int64_t lmax, int64_t nm, const int64_t* mval, const 
       for (int64_t mi = 0; mi < nm; ++mi) {
         int64_t m = mval[mi];
         ld th = (ld)theta[ir];
+        if (g_apply_cut && m > orc_mlim(lmax, spin, theta[ir])) {
+          for (int c = 0; c < (spin == 0 ? 1 : 2); ++c) {
+            ld* o = leg + 2 * ((c * nring + ir) * nm + mi);
+            o[0] = 0;
+            o[1] = 0;
+          }
+          continue;
+        }
         if (spin == 0) {
           lam_row_spin0(lmax, m, th, lp);
           ld sr = 0, si = 0;
@@ -338,6 +370,7 @@ void orc_leg2alm(int spin, int64_t lmax, int64_t nm, const int64_t* mval, const 
       }
       for (int64_t ir = 0; ir < nring; ++ir) {
         ld th = (ld)theta[ir];
+        if (g_apply_cut && m > orc_mlim(lmax, spin, theta[ir])) continue;
         if (spin == 0) {
           lam_row_spin0(lmax, m, th, lp);
           const ld* g = leg + 2 * ((0 * nring + ir) * nm + mi);
