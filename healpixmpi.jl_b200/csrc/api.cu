@@ -133,6 +133,13 @@ struct hpsht_plan {
   std::vector<int64_t> aoff, boff;  // block offsets in complex elements (max_ncomp sized)
   DevBuf<int64_t> d_boff;
   DevBuf<double> stage_alm, stage_map;  // device staging for host-pointer calls
+  // single-rank host-pointer calls: ring blocks pipelined against the PCIe copies of the map
+  int HB = 1;
+  std::vector<std::unique_ptr<RingFFT>> fftb;
+  std::vector<int64_t> blk_pix;         // first pixel of each block's (contiguous) pixel range, + end
+  std::vector<cudaEvent_t> ev_blk;
+  cudaStream_t hstream = nullptr;       // host <-> device copies
+  cudaEvent_t ev_hdone = nullptr;
   ncclComm_t comm = nullptr;
   std::unique_ptr<Timer> tm;
   double ms[HPSHT_NTIMES] = {0};
@@ -258,6 +265,37 @@ void hpsht_plan::ensure_stages() {
   leg.setup(lmax, mval.data(), mstart.data(), nm_loc, nr_tot, thetatot.data(), lay, max_ncomp, stream);
   HP_REQUIRE(P == 1 || leg.nslabs() == K, HPSHT_ERR_INTERNAL, "slab count mismatch");
   fft.setup(nr_loc, nphi.data(), phi0.data(), rstart.data(), nm_tot, stream);
+  if (P == 1) {
+    // Host-pointer calls move 8 B per pixel and component over PCIe, ~0.6x the time the transform
+    // itself needs at nside 4096.  With the rings cut into HB blocks of equal pixel count the copy of
+    // one block overlaps the Legendre + FFT work of the next (HPSHT_HOST_BLOCKS, 1 = off).
+    const char* eb = getenv("HPSHT_HOST_BLOCKS");
+    int want = eb ? std::max(1, atoi(eb)) : 8;
+    if (!eb && npix_loc < (1 << 22)) want = 1;  // small maps: the copies are microseconds
+    std::vector<double> w((size_t)nr_loc);
+    for (int64_t i = 0; i < nr_loc; ++i) w[(size_t)i] = (double)nphi[(size_t)i];
+    HB = leg.setup_blocks(want, w.data());
+    if (HB > 1) {
+      blk_pix.assign((size_t)HB + 1, 0);
+      fftb.clear();
+      for (int b = 0; b < HB; ++b) {
+        int64_t lo, hi;
+        leg.block_slots(b, &lo, &hi);
+        blk_pix[(size_t)b] = rstart[(size_t)lo];
+        // blocks run pole -> equator, i.e. towards lower slots: block b ends where block b-1 starts
+        const int64_t pend = hi < nr_loc ? rstart[(size_t)hi] : npix_loc;
+        if (b == 0) blk_pix[(size_t)HB] = pend;
+        HP_REQUIRE(b == 0 || pend == blk_pix[(size_t)b - 1], HPSHT_ERR_INTERNAL, "ring blocks are not contiguous");
+        fftb.emplace_back(new RingFFT());
+        fftb.back()->setup(hi - lo, nphi.data() + lo, phi0.data() + lo, rstart.data() + lo, nm_tot, stream, lo,
+                           nr_loc);
+      }
+      ev_blk.resize((size_t)HB);
+      for (auto& e : ev_blk) HP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      HP_CUDA(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
+      HP_CUDA(cudaEventCreateWithFlags(&ev_hdone, cudaEventDisableTiming));
+    }
+  }
   HP_CUDA(cudaStreamSynchronize(stream));
   stages_ready = true;
 }
@@ -312,7 +350,15 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
   HP_CUDA(cudaEventRecord(e[0], stream));
   const double* d_in = in;
   double* d_out = out;
-  if (!in_dev) {
+  // pixel range [lo, hi) of ring block b (blocks are numbered pole -> equator = descending pixels)
+  auto blk_lo = [&](int b) { return blk_pix[(size_t)b]; };
+  auto blk_hi = [&](int b) { return b == 0 ? blk_pix[(size_t)HB] : blk_pix[(size_t)b - 1]; };
+  const bool pipe_out = P == 1 && HB > 1 && synthesis && !out_dev;
+  const bool pipe_in = P == 1 && HB > 1 && !synthesis && !in_dev;
+  if (pipe_in) {
+    stage_map.ensure(map_d);
+    d_in = stage_map.p;
+  } else if (!in_dev) {
     DevBuf<double>& sb = synthesis ? stage_alm : stage_map;
     sb.ensure(synthesis ? alm_d : map_d);
     HP_CUDA(cudaMemcpyAsync(sb.p, in, (synthesis ? alm_d : map_d) * sizeof(double),
@@ -335,7 +381,31 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
   G.ncs = max_ncomp;
   if (synthesis) {
     // alm2leg (src/sht.jl:85)
-    if (P == 1) {
+    if (pipe_out) {
+      // all kernels first (a pageable destination makes cudaMemcpyAsync block the host), then the copies
+      leg.alm2leg_begin(d_in, nalm_loc, legF.p, (int64_t)max_ncomp * nr_loc * nm_tot, ncomp, stream);
+      for (int b = 0; b < HB; ++b) {
+        leg.alm2leg_block(b, legF.p, ncomp, stream, b == HB - 1);
+        if (b == HB - 1) {
+          HP_CUDA(cudaEventRecord(e[2], stream));
+          HP_CUDA(cudaEventRecord(e[3], stream));
+        }
+        fftb[(size_t)b]->leg2map(legF.p, d_out, npix_loc, ncomp, stream);
+        HP_CUDA(cudaEventRecord(ev_blk[(size_t)b], stream));
+      }
+      HP_CUDA(cudaEventRecord(e[4], stream));
+      for (int b = 0; b < HB; ++b) {
+        HP_CUDA(cudaStreamWaitEvent(hstream, ev_blk[(size_t)b], 0));
+        for (int c = 0; c < ncomp; ++c) {
+          const size_t o = (size_t)c * npix_loc + (size_t)blk_lo(b);
+          HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, (size_t)(blk_hi(b) - blk_lo(b)) * sizeof(double),
+                                  cudaMemcpyDeviceToHost, hstream));
+        }
+        extra += 0;
+      }
+      HP_CUDA(cudaEventRecord(ev_hdone, hstream));
+      HP_CUDA(cudaStreamWaitEvent(stream, ev_hdone, 0));
+    } else if (P == 1) {
       leg.alm2leg(d_in, nalm_loc, legF.p, (int64_t)max_ncomp * nr_loc * nm_tot, ncomp, stream);
       HP_CUDA(cudaEventRecord(e[2], stream));
       HP_CUDA(cudaEventRecord(e[3], stream));
@@ -359,7 +429,30 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
       HP_CUDA(cudaEventRecord(e[3], stream));  // exposed (non-overlapped) exchange tail + unpack
     }
     // leg2map (src/sht.jl:93)
-    fft.leg2map(legF.p, d_out, npix_loc, ncomp, stream);
+    if (!pipe_out) {
+      fft.leg2map(legF.p, d_out, npix_loc, ncomp, stream);
+      HP_CUDA(cudaEventRecord(e[4], stream));
+    }
+  } else if (pipe_in) {
+    // block b: host-to-device copy on the copy stream, then map2leg + leg2alm of that block; the small
+    // equator-most blocks go first so that the compute starts early
+    leg.leg2alm_blocks_begin(ncomp, stream);
+    for (int b = HB - 1; b >= 0; --b) {
+      for (int c = 0; c < ncomp; ++c) {
+        const size_t o = (size_t)c * npix_loc + (size_t)blk_lo(b);
+        HP_CUDA(cudaMemcpyAsync(stage_map.p + o, in + o, (size_t)(blk_hi(b) - blk_lo(b)) * sizeof(double),
+                                cudaMemcpyHostToDevice, hstream));
+      }
+      HP_CUDA(cudaEventRecord(ev_blk[(size_t)b], hstream));
+      HP_CUDA(cudaStreamWaitEvent(stream, ev_blk[(size_t)b], 0));
+      fftb[(size_t)b]->map2leg(d_in, npix_loc, legF.p, ncomp, stream);
+      if (b == HB - 1) {
+        HP_CUDA(cudaEventRecord(e[2], stream));
+        HP_CUDA(cudaEventRecord(e[3], stream));
+      }
+      leg.leg2alm_block(b, legF.p, ncomp, stream, b == 0);
+    }
+    leg.leg2alm_blocks_end(d_out, nalm_loc, ncomp, stream);
     HP_CUDA(cudaEventRecord(e[4], stream));
   } else {
     // map2leg (src/sht.jl:169)
@@ -399,7 +492,7 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
     }
     HP_CUDA(cudaEventRecord(e[4], stream));
   }
-  if (!out_dev)
+  if (!out_dev && !pipe_out)
     HP_CUDA(cudaMemcpyAsync(out, d_out, (synthesis ? map_d : alm_d) * sizeof(double),
                             cudaMemcpyDeviceToHost, stream));
   HP_CUDA(cudaEventRecord(e[5], stream));
@@ -424,6 +517,10 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
   }
   ms[1] = leg.main_kernel_ms();
   n_launch = leg.launches() + fft.launches() + extra;
+  for (auto& f : fftb) {
+    n_launch += f->launches();
+    f->reset_launches();
+  }
 }
 
 // =================================================================================================
@@ -799,6 +896,9 @@ int hpsht_plan_destroy(hpsht_plan* plan) {
       cudaStreamDestroy(st);
     }
     if (plan->ev_ready) cudaEventDestroy(plan->ev_ready);
+    for (auto& e : plan->ev_blk) cudaEventDestroy(e);
+    if (plan->ev_hdone) cudaEventDestroy(plan->ev_hdone);
+    if (plan->hstream) cudaStreamDestroy(plan->hstream);
     if (plan->cstream) cudaStreamDestroy(plan->cstream);
     if (plan->stream) cudaStreamDestroy(plan->stream);
     delete plan;

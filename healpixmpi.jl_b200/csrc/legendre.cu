@@ -185,6 +185,7 @@ struct LegParams {
   double* leg;            // complex128 (synthesis out / adjoint in)
   double* part;           // adjoint partial sums, 4 doubles / step
   const int64_t* partoff; // per item: offset in steps into part
+  int accumulate;         // adjoint: 1 = the partial sums of this item already hold earlier ring blocks
 };
 
 __device__ __forceinline__ int64_t leg_rowoff(const LegParams& P, int p, int mi) {
@@ -1169,7 +1170,7 @@ __global__ void __launch_bounds__(32) k_leg2alm_s0_w(LegParams P) {
       double* gp = gpart + (size_t)c * LEG_CHUNK * 4 + lane;
       double old[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) old[k] = (tile > 0) ? gp[k * 32] : 0.0;
+      for (int k = 0; k < 8; ++k) old[k] = (tile > 0 || P.accumulate) ? gp[k * 32] : 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) s_res[k * 32 + lane] = 0.0;  // groups that only ramp contribute 0
       mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
@@ -1370,7 +1371,7 @@ __global__ void __launch_bounds__(32) k_leg2alm_s2_w(LegParams P) {
       double* gp = gpart + (size_t)c * LEG_CHUNK * 4 + lane;
       double old[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) old[k] = (tile > 0) ? gp[k * 32] : 0.0;
+      for (int k = 0; k < 8; ++k) old[k] = (tile > 0 || P.accumulate) ? gp[k * 32] : 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) s_res[k * 32 + lane] = 0.0;  // groups that only ramp contribute 0
       mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
@@ -1843,6 +1844,215 @@ void LegendreStage::setup(int64_t lmax, const int64_t* mval, const int64_t* msta
   have0_ = have2_ = false;
 }
 
+static inline int64_t max_of(const std::vector<int64_t>& v) {
+  int64_t m = 0;
+  for (int64_t x : v) m = std::max(m, x);
+  return m;
+}
+
+// ---- ring blocks -----------------------------------------------------------------------------
+static int64_t gcd_i(int64_t a, int64_t b) { return b == 0 ? a : gcd_i(b, a % b); }
+
+int LegendreStage::setup_blocks(int want, const double* slot_weight) {
+  blk_pair_.clear();
+  const int np = (int)npairs_;
+  if (want < 1 || !adj_warp_mode()) want = 1;
+  blk_pair_.push_back(0);
+  // Preferred cut: every multiple of the least common multiple of the four kernels' tile sizes, so
+  // that no block ends in a partly filled tile (1536 pairs with the default configurations: six
+  // blocks at nside 4096, the equator-most one -- whose copy cannot hide behind compute -- the
+  // smallest).  Too many blocks: merge from the pole, where blocks hold the fewest pixels.
+  int64_t align = 32;
+  for (int t : {kSynCfgs[s0_cfg()].R * kSynCfgs[s0_cfg()].NW * 32, kSynCfgs[s2_cfg()].R * kSynCfgs[s2_cfg()].NW * 32,
+                adj_tile(0), adj_tile(2)})
+    align = align / gcd_i(align, t) * t;
+  if (want > 1 && np >= 2 * align) {
+    for (int64_t p = align; p < np; p += align) blk_pair_.push_back((int)p);
+    while ((int)blk_pair_.size() > want) blk_pair_.erase(blk_pair_.begin() + 1);
+  } else if (want > 1) {
+    // small problems (tests): equal-weight blocks on warp-aligned boundaries
+    std::vector<double> cum((size_t)np + 1, 0.0);
+    for (int p = 0; p < np; ++p) {
+      double w = slot_weight[pairs_[(size_t)p].slotN];
+      if (pairs_[(size_t)p].slotS >= 0) w += slot_weight[pairs_[(size_t)p].slotS];
+      cum[(size_t)p + 1] = cum[(size_t)p] + w;
+    }
+    for (int b = 1; b < want; ++b) {
+      const double target = cum[(size_t)np] * b / want;
+      int p = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+      p = (p + 31) / 32 * 32;
+      if (p > blk_pair_.back() && p < np) blk_pair_.push_back(p);
+    }
+  }
+  blk_pair_.push_back(np);
+  // a block's slots must be contiguous for the caller's copies
+  for (int b = 0; b + 1 < (int)blk_pair_.size(); ++b) {
+    int64_t lo, hi;
+    block_slots(b, &lo, &hi);
+    int64_t cnt = 0;
+    for (int p = blk_pair_[(size_t)b]; p < blk_pair_[(size_t)b + 1]; ++p) cnt += pairs_[(size_t)p].slotS >= 0 ? 2 : 1;
+    if (cnt != hi - lo) {  // exotic ring order: no blocking
+      blk_pair_.assign({0, np});
+      break;
+    }
+  }
+  have0_ = have2_ = false;
+  return nblocks();
+}
+
+void LegendreStage::block_slots(int b, int64_t* slot_lo, int64_t* slot_hi) const {
+  int64_t lo = INT64_MAX, hi = -1;
+  for (int p = blk_pair_[(size_t)b]; p < blk_pair_[(size_t)b + 1]; ++p) {
+    const PairHost& q = pairs_[(size_t)p];
+    lo = std::min(lo, q.slotN);
+    hi = std::max(hi, q.slotN);
+    if (q.slotS >= 0) {
+      lo = std::min(lo, q.slotS);
+      hi = std::max(hi, q.slotS);
+    }
+  }
+  *slot_lo = lo;
+  *slot_hi = hi + 1;
+}
+
+// per block: synthesis = one item per active tile; adjoint = one item per m covering the block's
+// active tiles, all blocks of an m accumulating into the same partial-sum row (offset off[mi])
+void LegendreStage::build_block_items(int spin, const LegendreTables& T, cudaStream_t stream) {
+  const bool s2 = spin != 0;
+  const std::vector<int64_t>& nstep = s2 ? T.nstep2 : T.nstep0;
+  const std::vector<int64_t>& off = s2 ? T.off2 : T.off0;
+  const int stile = kSynCfgs[s2 ? s2_cfg() : s0_cfg()].R * kSynCfgs[s2 ? s2_cfg() : s0_cfg()].NW * 32;
+  const int atile = adj_tile(spin);
+  std::vector<WorkItem> si, ai;
+  std::vector<int64_t> apo;
+  std::vector<int> rs, ra;
+  for (int b = 0; b < nblocks(); ++b) {
+    rs.push_back((int)si.size());
+    ra.push_back((int)ai.size());
+    const int pa = blk_pair_[(size_t)b], pb = blk_pair_[(size_t)b + 1];
+    auto tile_max = [&](int tile) {
+      const int nt = (pb - pa + tile - 1) / tile;
+      std::vector<int> tm((size_t)nt, -1);
+      for (int t = 0; t < nt; ++t)
+        for (int p = pa + t * tile; p < std::min(pb, pa + (t + 1) * tile); ++p)
+          tm[(size_t)t] = std::max(tm[(size_t)t], s2 ? pairs_[(size_t)p].mlim2 : pairs_[(size_t)p].mlim0);
+      return tm;
+    };
+    const std::vector<int> tms = tile_max(stile), tma = tile_max(atile);
+    for (size_t mi = 0; mi < mval_.size(); ++mi) {
+      if (nstep[mi] <= 0) continue;
+      for (int t = (int)tms.size() - 1; t >= 0; --t) {
+        if (tms[(size_t)t] < mval_[mi]) continue;
+        WorkItem w;
+        w.mi = (int)mi;
+        w.p0 = pa + t * stile;
+        w.np = std::min(pb, pa + (t + 1) * stile) - w.p0;
+        w.part = 0;
+        si.push_back(w);
+      }
+      int tlo = -1, thi = -1;
+      for (int t = 0; t < (int)tma.size(); ++t)
+        if (tma[(size_t)t] >= mval_[mi]) {
+          if (tlo < 0) tlo = t;
+          thi = t;
+        }
+      if (tlo >= 0) {
+        WorkItem w;
+        w.mi = (int)mi;
+        w.p0 = pa + tlo * atile;
+        w.np = std::min(pb, pa + (thi + 1) * atile) - w.p0;
+        w.part = 0;
+        ai.push_back(w);
+        apo.push_back(off[mi]);
+      }
+    }
+  }
+  rs.push_back((int)si.size());
+  ra.push_back((int)ai.size());
+  (s2 ? d_bitems_s2_ : d_bitems_s0_).upload(si.data(), si.size(), stream);
+  (s2 ? d_bitems_a2_ : d_bitems_a0_).upload(ai.data(), ai.size(), stream);
+  (s2 ? d_bpartoff2_ : d_bpartoff0_).upload(apo.data(), apo.size(), stream);
+  (s2 ? brange_s2_ : brange_s0_) = rs;
+  (s2 ? brange_a2_ : brange_a0_) = ra;
+  HP_CUDA(cudaStreamSynchronize(stream));
+}
+
+void LegendreStage::alm2leg_block(int b, double* d_leg, int ncomp, cudaStream_t stream, bool last) {
+  const int spin = ncomp == 1 ? 0 : 2;
+  const std::vector<int>& br = spin == 0 ? brange_s0_ : brange_s2_;
+  const int first = br[(size_t)b], count = br[(size_t)b + 1] - first;
+  if (count > 0) {
+    LegParams P;
+    fill_params(P, spin, false);
+    P.items = (spin == 0 ? d_bitems_s0_.p : d_bitems_s2_.p) + first;
+    P.leg = d_leg;
+    if (spin == 0)
+      HP_LAUNCH(k_alm2leg_s0, env_syn_prod(), s0_cfg(), count, stream, P);
+    else
+      HP_LAUNCH(k_alm2leg_s2, env_syn_prod(), s2_cfg(), count, stream, P);
+    ++launches_;
+    HP_CUDA(cudaGetLastError());
+  }
+  if (last) cudaEventRecord(ev1_, stream);
+}
+
+void LegendreStage::leg2alm_blocks_begin(int ncomp, cudaStream_t stream) {
+  const int spin = ncomp == 1 ? 0 : 2;
+  ensure_spin(spin, stream);
+  HP_REQUIRE(adj_warp_mode(), HPSHT_ERR_UNSUPPORTED, "ring blocks need the single-warp adjoint kernels");
+  const size_t need = accum_steps_need_ * 4;
+  d_part_.ensure(std::max(part_steps_need_ * 4, need));
+  const int64_t total = (spin == 0 ? off0_h_ : off2_h_)[(size_t)nm_];
+  HP_CUDA(cudaMemsetAsync(d_part_.p, 0, (size_t)total * 4 * sizeof(double), stream));
+  cudaEventRecord(ev0_, stream);
+}
+
+void LegendreStage::leg2alm_block(int b, const double* d_leg, int ncomp, cudaStream_t stream, bool last) {
+  const int spin = ncomp == 1 ? 0 : 2;
+  const std::vector<int>& br = spin == 0 ? brange_a0_ : brange_a2_;
+  const int first = br[(size_t)b], count = br[(size_t)b + 1] - first;
+  if (count > 0) {
+    LegParams P;
+    fill_params(P, spin, true);
+    P.items = (spin == 0 ? d_bitems_a0_.p : d_bitems_a2_.p) + first;
+    P.partoff = (spin == 0 ? d_bpartoff0_.p : d_bpartoff2_.p) + first;
+    P.leg = const_cast<double*>(d_leg);
+    P.accumulate = 1;
+    if (spin == 0)
+      HP_LAUNCH_W(k_leg2alm_s0_w, a0w_R(), count, stream, P);
+    else
+      HP_LAUNCH_W(k_leg2alm_s2_w, a2w_R(), count, stream, P);
+    ++launches_;
+    HP_CUDA(cudaGetLastError());
+  }
+  if (last) cudaEventRecord(ev1_, stream);
+}
+
+// the per-m rows of d_part_ are laid out like d_accum_ (offset off[mi]): post-process them directly
+void LegendreStage::leg2alm_blocks_end(double* d_alm, int64_t alm_cstride, int ncomp, cudaStream_t stream) {
+  const int spin = ncomp == 1 ? 0 : 2;
+  const int TB = 256;
+  if (spin == 0) {
+    const int64_t mx = max_of(nstep0_h_);
+    if (mx > 0) {
+      dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
+      k_post_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p), d_mval_.p, d_mstart_.p,
+                                         d_nstep0_.p, d_off0_.p, d_invs0_.p, lmax_,
+                                         reinterpret_cast<double2*>(d_alm));
+      ++launches_;
+    }
+  } else {
+    int64_t mx = std::max<int64_t>(max_of(nstep2_h_), 1);
+    dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
+    k_post_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p), d_mval_.p, d_mstart_.p,
+                                       d_nstep2_.p, d_off2_.p, d_sig2_.p, lmax_,
+                                       reinterpret_cast<double2*>(d_alm),
+                                       reinterpret_cast<double2*>(d_alm) + alm_cstride);
+    ++launches_;
+  }
+  HP_CUDA(cudaGetLastError());
+}
+
 // first item of every m-slab (items are ordered by local m index)
 static std::vector<int> slab_item_ranges(const std::vector<WorkItem>& items, const std::vector<int>& slab_first_mi) {
   std::vector<int> r(slab_first_mi.size(), (int)items.size());
@@ -1915,16 +2125,11 @@ void LegendreStage::ensure_spin(int spin, cudaStream_t stream) {
     srange_a2_ = slab_item_ranges(items_a2_, slab_first_mi_);
     have2_ = true;
   }
+  if (nblocks() > 1) build_block_items(spin, T, stream);
   part_steps_need_ = std::max(part_steps_need_, part_steps);
   accum_steps_need_ = std::max(accum_steps_need_,
                                (size_t)(spin == 0 ? T.off0[(size_t)nm_] : T.off2[(size_t)nm_]));
   HP_CUDA(cudaStreamSynchronize(stream));  // host vectors of T die here
-}
-
-static inline int64_t max_of(const std::vector<int64_t>& v) {
-  int64_t m = 0;
-  for (int64_t x : v) m = std::max(m, x);
-  return m;
 }
 
 void LegendreStage::fill_params(LegParams& P, int spin, bool adjoint) const {

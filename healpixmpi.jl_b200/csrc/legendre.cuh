@@ -75,6 +75,20 @@ class LegendreStage {
   // re-records the end-of-main-kernel timing event (when slab kernels ran on other streams)
   void mark_main_end(cudaStream_t stream);
 
+  // Ring blocks: the pole -> equator pair list cut into <= `want` contiguous ranges of about equal
+  // weight (slot_weight[slot], e.g. pixels per ring).  A block's rings occupy a contiguous slot range,
+  // so the caller can pipeline  Legendre(block) -> ring FFT(block) -> device-to-host copy(block)  and
+  // the reverse for the adjoint.  Call right after setup(); returns the number of blocks made.
+  int setup_blocks(int want, const double* slot_weight);
+  int nblocks() const { return (int)blk_pair_.size() - 1; }
+  void block_slots(int b, int64_t* slot_lo, int64_t* slot_hi) const;   // [slot_lo, slot_hi)
+  // synthesis: alm2leg_begin, then every block once in any order
+  void alm2leg_block(int b, double* d_leg, int ncomp, cudaStream_t stream, bool last);
+  // adjoint: leg2alm_blocks_begin, every block once (same stream), leg2alm_blocks_end
+  void leg2alm_blocks_begin(int ncomp, cudaStream_t stream);
+  void leg2alm_block(int b, const double* d_leg, int ncomp, cudaStream_t stream, bool last);
+  void leg2alm_blocks_end(double* d_alm, int64_t alm_cstride, int ncomp, cudaStream_t stream);
+
   double steps_culled(int spin) const { return spin ? culled2_ : culled0_; }
   double steps_dense() const { return dense_; }
   int64_t launches() const { return launches_; }
@@ -121,6 +135,12 @@ class LegendreStage {
   DevBuf<int> d_afirst0_, d_acount0_, d_afirst2_, d_acount2_;
   DevBuf<int64_t> d_apartoff0_, d_apartoff2_;                // per adjoint item: offset into d_part_ (steps)
   std::vector<int64_t> apartoff0_, apartoff2_;
+  // ring-block work lists
+  std::vector<int> blk_pair_;                                    // first pair of each block (+ end)
+  std::vector<int> brange_s0_, brange_s2_, brange_a0_, brange_a2_;
+  DevBuf<WorkItem> d_bitems_s0_, d_bitems_s2_, d_bitems_a0_, d_bitems_a2_;
+  DevBuf<int64_t> d_bpartoff0_, d_bpartoff2_;
+  void build_block_items(int spin, const LegendreTables& T, cudaStream_t stream);
 };
 
 // Generic N/S pair detection on an arbitrary theta list (pole -> equator order).

@@ -796,9 +796,22 @@ int next_pow2(int v) {
 
 }  // namespace
 
+// dynamic-smem opt-in is per kernel, not per RingFFT object: only ever raise it
+// (the attribute is per device; one table row per device ordinal)
+static void raise_smem_attr(const void* fn, size_t* cur_by_dev, size_t want) {
+  int dev = 0;
+  HP_CUDA(cudaGetDevice(&dev));
+  size_t* cur = &cur_by_dev[dev & 63];
+  if (want <= *cur) return;
+  HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+  *cur = want;
+}
+static size_t g_smem_leg2map[64] = {0}, g_smem_map2leg[64] = {0}, g_smem_hhat[64] = {0};
+
 void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, const int64_t* ringstart,
-                    int64_t nm, cudaStream_t stream) {
-  nring_ = nring;
+                    int64_t nm, cudaStream_t stream, int64_t slot0, int64_t leg_nring) {
+  nring_ = leg_nring > 0 ? leg_nring : nring;
+  nrings_own_ = nring;
   nm_ = nm;
   npix_ = 0;
   desc_.clear();
@@ -820,7 +833,7 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     RingDesc d;
     d.pixoff = ringstart[i];
     d.phi0 = phi0[i];
-    d.ir = (int)i;
+    d.ir = (int)(slot0 + i);
     d.nphi = (int)n;
     d.r = (int)(n / 4);
     const bool pow2 = (d.r & (d.r - 1)) == 0;
@@ -917,10 +930,8 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
   size_t max_smem = 0;
   for (auto& c : classes_) max_smem = std::max(max_smem, c.smem);
   HP_REQUIRE(max_smem <= 227 * 1024, HPSHT_ERR_UNSUPPORTED, "ring too long for the in-smem FFT");
-  if (max_smem > 0) {
-    HP_CUDA(cudaFuncSetAttribute(k_leg2map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    HP_CUDA(cudaFuncSetAttribute(k_map2leg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-  }
+  raise_smem_attr((const void*)k_leg2map, g_smem_leg2map, max_smem);
+  raise_smem_attr((const void*)k_map2leg, g_smem_map2leg, max_smem);
   // chirp spectra
   d_hhat_.alloc((size_t)std::max<int64_t>(htotal, 1) * 2);
   if (!rs.empty()) {
@@ -936,7 +947,7 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     }
     const int nt = 256;
     const size_t sm = smem_bytes(rmax, Mmax, nt);
-    HP_CUDA(cudaFuncSetAttribute(k_build_hhat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    raise_smem_attr((const void*)k_build_hhat, g_smem_hhat, sm);
     k_build_hhat<<<(unsigned)rs.size(), nt, sm, stream>>>(
         d_rs.p, d_Ms.p, d_hoffs.p, reinterpret_cast<double2*>(d_hhat_.p),
         rmax, Mmax);

@@ -34,8 +34,10 @@ class RingFFT {
   RingFFT(const RingFFT&) = delete;
   RingFFT& operator=(const RingFFT&) = delete;
 
+  // slot0 / leg_nring: the nring rings are slots slot0 .. slot0+nring-1 of a leg array that holds
+  // leg_nring rings per component (defaults: the whole array)
   void setup(int64_t nring, const int64_t* nphi, const double* phi0, const int64_t* ringstart,
-             int64_t nm, cudaStream_t stream);
+             int64_t nm, cudaStream_t stream, int64_t slot0 = 0, int64_t leg_nring = -1);
   // device pointers
   void leg2map(const double* d_leg, double* d_map, int64_t map_cstride, int ncomp,
                cudaStream_t stream);
@@ -45,7 +47,7 @@ class RingFFT {
   int64_t launches() const { return launches_; }
   void reset_launches() { launches_ = 0; }
   // algorithmic HBM bytes of one component, one direction: 16*nm*nring + 8*npix
-  double algorithmic_bytes() const { return 16.0 * (double)nm_ * (double)nring_ + 8.0 * (double)npix_; }
+  double algorithmic_bytes() const { return 16.0 * (double)nm_ * (double)nrings_own_ + 8.0 * (double)npix_; }
 
  private:
   struct Class {
@@ -54,7 +56,7 @@ class RingFFT {
     size_t smem = 0;
     int rmax = 0, Mmax = 0;
   };
-  int64_t nring_ = 0, nm_ = 0, npix_ = 0;
+  int64_t nring_ = 0, nrings_own_ = 0, nm_ = 0, npix_ = 0;
   int64_t launches_ = 0;
   void ensure_long_scratch(int ncomp);
   std::vector<RingDesc> desc_, desc_long_;
