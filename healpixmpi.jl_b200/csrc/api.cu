@@ -267,10 +267,10 @@ void hpsht_plan::ensure_stages() {
   fft.setup(nr_loc, nphi.data(), phi0.data(), rstart.data(), nm_tot, stream);
   if (P == 1) {
     // Host-pointer calls move 8 B per pixel and component over PCIe, ~0.6x the time the transform
-    // itself needs at nside 4096.  With the rings cut into HB blocks of equal pixel count the copy of
+    // itself needs at nside 4096.  With the rings cut into HB tile-aligned blocks the copy of
     // one block overlaps the Legendre + FFT work of the next (HPSHT_HOST_BLOCKS, 1 = off).
     const char* eb = getenv("HPSHT_HOST_BLOCKS");
-    int want = eb ? std::max(1, atoi(eb)) : 8;
+    int want = eb ? std::max(1, atoi(eb)) : 6;
     if (!eb && npix_loc < (1 << 22)) want = 1;  // small maps: the copies are microseconds
     std::vector<double> w((size_t)nr_loc);
     for (int64_t i = 0; i < nr_loc; ++i) w[(size_t)i] = (double)nphi[(size_t)i];

@@ -318,6 +318,19 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
     er[r] = ei[r] = orr[r] = oi[r] = 0.0;
   }
   const bool warp_act = __any_sync(0xffffffffu, any_act);
+  // warp-uniform range flags, re-voted only when a scale changes (not once per group)
+  bool w_any0 = false, w_neg = false;
+  auto revote = [&]() {
+    bool mine0 = false, mineneg = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mine0 |= act[r] && (sc[r] == 0);
+      mineneg |= (sc[r] < 0);
+    }
+    w_any0 = __any_sync(0xffffffffu, mine0);
+    w_neg = __any_sync(0xffffffffu, mineneg);
+  };
+  revote();
 
   for (int c = 0; c < nchunks; ++c) {
     const int st = c % NSTAGE;
@@ -329,15 +342,8 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
     if (warp_act) {
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
       for (int g = 0; g < ng; ++g) {
-        bool mine0 = false, mineneg = false;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          mine0 |= act[r] && (sc[r] == 0);
-          mineneg |= (sc[r] < 0);
-        }
-        const bool any0 = __any_sync(0xffffffffu, mine0);
         const Coef* cf = &s_coef[st][g * LEG_GROUP];
-        if (any0) {
+        if (w_any0) {
           const Strm* sm = &s_strm[st][g * LEG_GROUP];
 #pragma unroll
           for (int s = 0; s < LEG_GROUP; ++s) {
@@ -368,7 +374,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
             }
           }
         }
-        if (__any_sync(0xffffffffu, mineneg)) {
+        if (w_neg) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if (sc[r] < 0 && is_big(lam2[r])) {
@@ -378,6 +384,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s0(LegParams P) {
               er[r] = ei[r] = orr[r] = oi[r] = 0.0;  // drop what was accumulated while scaled
             }
           }
+          revote();  // scales changed: refresh the warp-uniform flags
         }
         if (PROD == 2 && issuer) pump.run(c);  // opportunistic refill, never blocks here
       }
@@ -480,6 +487,19 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
     psr[r] = psi[r] = msr[r] = msi[r] = 0.0;
   }
   const bool warp_act = __any_sync(0xffffffffu, any_act);
+  // warp-uniform range flags, re-voted only when a scale changes (not once per group)
+  bool w_any0 = false, w_neg = false;
+  auto revote = [&]() {
+    bool mine0 = false, mineneg = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mine0 |= act[r] && ((scp[r] == 0) || (scm[r] == 0));
+      mineneg |= (scp[r] < 0) || (scm[r] < 0);
+    }
+    w_any0 = __any_sync(0xffffffffu, mine0);
+    w_neg = __any_sync(0xffffffffu, mineneg);
+  };
+  revote();
 
   for (int c = 0; c < nchunks; ++c) {
     const int st = c % NSTAGE;
@@ -491,15 +511,8 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
     if (warp_act) {
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
       for (int g = 0; g < ng; ++g) {
-        bool mine0 = false, mineneg = false;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          mine0 |= act[r] && ((scp[r] == 0) || (scm[r] == 0));
-          mineneg |= (scp[r] < 0) || (scm[r] < 0);
-        }
-        const bool any0 = __any_sync(0xffffffffu, mine0);
         const Coef* cf = &s_coef[st][g * LEG_GROUP];
-        if (any0) {
+        if (w_any0) {
           const Strm* sm = &s_strm[st][g * LEG_GROUP];
 #pragma unroll
           for (int s = 0; s < LEG_GROUP; ++s) {
@@ -549,7 +562,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
             }
           }
         }
-        if (__any_sync(0xffffffffu, mineneg)) {
+        if (w_neg) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if (scp[r] < 0 && is_big(lp2[r])) {
@@ -565,6 +578,7 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
               mnr[r] = mni[r] = psr[r] = psi[r] = 0.0;
             }
           }
+          revote();  // scales changed: refresh the warp-uniform flags
         }
         if (PROD == 2 && issuer) pump.run(c);
       }
@@ -1086,7 +1100,7 @@ struct WarpPipe {
 };
 
 template <int R, int DBG = 0>
-__global__ void __launch_bounds__(32) k_leg2alm_s0_w(LegParams P) {
+__global__ void __launch_bounds__(32, (R <= 4) ? 16 : (R <= 6 ? 12 : 1)) k_leg2alm_s0_w(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ double s_tr[16][33];
   __shared__ double s_res[LEG_CHUNK * 4];  // reduced sums of the current chunk
@@ -1159,6 +1173,19 @@ __global__ void __launch_bounds__(32) k_leg2alm_s0_w(LegParams P) {
       if (act[r] && sc[r] == 0) load_in(r, p);
     }
     const bool warp_act = __any_sync(0xffffffffu, any_act);
+    // warp-uniform range flags, re-voted only when a scale changes (not once per group)
+    bool w_any0 = false, w_neg = false;
+    auto revote = [&]() {
+      bool mine0 = false, mineneg = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        mine0 |= act[r] && (sc[r] == 0);
+        mineneg |= (sc[r] < 0);
+      }
+      w_any0 = __any_sync(0xffffffffu, mine0);
+      w_neg = __any_sync(0xffffffffu, mineneg);
+    };
+    revote();
 
     for (int c = 0; c < nchunks; ++c, ++cg) {
       const int st = cg % NSTAGE;
@@ -1179,15 +1206,8 @@ __global__ void __launch_bounds__(32) k_leg2alm_s0_w(LegParams P) {
 #pragma unroll 1
         for (int g = 0; g < ng; ++g) {
           {
-            bool mine0 = false, mineneg = false;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              mine0 |= act[r] && (sc[r] == 0);
-              mineneg |= (sc[r] < 0);
-            }
-            const bool any0 = __any_sync(0xffffffffu, mine0);
             const Coef* cf = &s_coef[st][g * LEG_GROUP];
-            if (any0) {
+            if (w_any0) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 double acc[16];
@@ -1234,7 +1254,7 @@ __global__ void __launch_bounds__(32) k_leg2alm_s0_w(LegParams P) {
                 }
               }
             }
-            if (__any_sync(0xffffffffu, mineneg)) {
+            if (w_neg) {
 #pragma unroll
               for (int r = 0; r < R; ++r) {
                 if (sc[r] < 0 && is_big(lam2[r])) {
@@ -1244,6 +1264,7 @@ __global__ void __launch_bounds__(32) k_leg2alm_s0_w(LegParams P) {
                   if (sc[r] == 0) load_in(r, tp0 + r * 32 + lane);
                 }
               }
+              revote();  // scales changed: refresh the warp-uniform flags
             }
           }
         }
@@ -1257,7 +1278,7 @@ __global__ void __launch_bounds__(32) k_leg2alm_s0_w(LegParams P) {
 }
 
 template <int R>
-__global__ void __launch_bounds__(32) k_leg2alm_s2_w(LegParams P) {
+__global__ void __launch_bounds__(32, (R <= 2) ? 16 : (R <= 3 ? 12 : (R <= 4 ? 10 : 1))) k_leg2alm_s2_w(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ double s_tr[16][33];
   __shared__ double s_res[LEG_CHUNK * 4];  // reduced sums of the current chunk
@@ -1361,6 +1382,19 @@ __global__ void __launch_bounds__(32) k_leg2alm_s2_w(LegParams P) {
       if (act[r] && scm[r] == 0) load_m(r, p);
     }
     const bool warp_act = __any_sync(0xffffffffu, any_act);
+    // warp-uniform range flags, re-voted only when a scale changes (not once per group)
+    bool w_any0 = false, w_neg = false;
+    auto revote = [&]() {
+      bool mine0 = false, mineneg = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        mine0 |= act[r] && ((scp[r] == 0) || (scm[r] == 0));
+        mineneg |= (scp[r] < 0) || (scm[r] < 0);
+      }
+      w_any0 = __any_sync(0xffffffffu, mine0);
+      w_neg = __any_sync(0xffffffffu, mineneg);
+    };
+    revote();
 
     for (int c = 0; c < nchunks; ++c, ++cg) {
       const int st = cg % NSTAGE;
@@ -1380,15 +1414,8 @@ __global__ void __launch_bounds__(32) k_leg2alm_s2_w(LegParams P) {
 #pragma unroll 1
         for (int g = 0; g < ng; ++g) {
           {
-            bool mine0 = false, mineneg = false;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              mine0 |= act[r] && ((scp[r] == 0) || (scm[r] == 0));
-              mineneg |= (scp[r] < 0) || (scm[r] < 0);
-            }
-            const bool any0 = __any_sync(0xffffffffu, mine0);
             const Coef* cf = &s_coef[st][g * LEG_GROUP];
-            if (any0) {
+            if (w_any0) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 double acc[16];
@@ -1444,7 +1471,7 @@ __global__ void __launch_bounds__(32) k_leg2alm_s2_w(LegParams P) {
                 }
               }
             }
-            if (__any_sync(0xffffffffu, mineneg)) {
+            if (w_neg) {
 #pragma unroll
               for (int r = 0; r < R; ++r) {
                 const int p = tp0 + r * 32 + lane;
@@ -1461,6 +1488,7 @@ __global__ void __launch_bounds__(32) k_leg2alm_s2_w(LegParams P) {
                   if (scm[r] == 0) load_m(r, p);
                 }
               }
+              revote();  // scales changed: refresh the warp-uniform flags
             }
           }
         }
@@ -1692,8 +1720,8 @@ static int a0_cfg() { return env_int("HPSHT_A0_CFG", 1); }  // block-mode adjoin
 static int a2_cfg() { return env_int("HPSHT_A2_CFG", 0); }  // block-mode adjoint <2,4>
 // adjoint kernel family: 1 = single-warp CTAs (k_leg2alm_*_w), 0 = 4-warp CTAs with a chunk barrier
 static int adj_warp_mode() { return env_int("HPSHT_ADJ_WARP", 1); }
-static int a0w_R() { return env_int("HPSHT_A0W_R", 6); }
-static int a2w_R() { return env_int("HPSHT_A2W_R", 3); }
+static int a0w_R() { return env_int("HPSHT_A0W_R", 8); }
+static int a2w_R() { return env_int("HPSHT_A2W_R", 4); }
 #define HP_LAUNCH_W(KERNEL, Rval, nitems, stream, P)                                                  \
   do {                                                                                                 \
     switch (Rval) {                                                                                    \
@@ -1858,15 +1886,18 @@ int LegendreStage::setup_blocks(int want, const double* slot_weight) {
   const int np = (int)npairs_;
   if (want < 1 || !adj_warp_mode()) want = 1;
   blk_pair_.push_back(0);
-  // Preferred cut: every multiple of the least common multiple of the four kernels' tile sizes, so
-  // that no block ends in a partly filled tile (1536 pairs with the default configurations: six
-  // blocks at nside 4096, the equator-most one -- whose copy cannot hide behind compute -- the
-  // smallest).  Too many blocks: merge from the pole, where blocks hold the fewest pixels.
+  // Preferred cut: multiples of the least common multiple of the four kernels' tile sizes (512 pairs
+  // with the default configurations), so that no block ends in a partly filled tile; about `want`
+  // blocks (nside 4096, want 6: 1536-pair blocks, the equator-most one -- whose copy cannot hide
+  // behind compute -- being the 512-pair remainder).  Too many blocks: merge from the pole, where
+  // blocks hold the fewest pixels.
   int64_t align = 32;
   for (int t : {kSynCfgs[s0_cfg()].R * kSynCfgs[s0_cfg()].NW * 32, kSynCfgs[s2_cfg()].R * kSynCfgs[s2_cfg()].NW * 32,
                 adj_tile(0), adj_tile(2)})
     align = align / gcd_i(align, t) * t;
   if (want > 1 && np >= 2 * align) {
+    const int64_t k = std::max<int64_t>(1, (np + want * align / 2) / (want * align));
+    if (np >= 2 * k * align) align *= k;
     for (int64_t p = align; p < np; p += align) blk_pair_.push_back((int)p);
     while ((int)blk_pair_.size() > want) blk_pair_.erase(blk_pair_.begin() + 1);
   } else if (want > 1) {
