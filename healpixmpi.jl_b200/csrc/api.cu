@@ -50,23 +50,22 @@ __device__ __forceinline__ int64_t mapside_off(const ExchGeom& g, const int64_t*
   const int64_t ns = min(ms, nm_s - ss);
   return boff[s] + g.nr_loc * ((int64_t)g.ncs * ss + (int64_t)comp * ns) + j * ns + (i - ss);
 }
+// rows j0 .. j0+nj-1 of every component (the whole array: j0 = 0, nj = nr_loc)
 __global__ void k_unpack(const double2* __restrict__ mapside, const int64_t* __restrict__ boff,
-                         double2* __restrict__ legF, ExchGeom g) {
+                         double2* __restrict__ legF, ExchGeom g, int64_t j0, int64_t nj) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = blockIdx.y;  // comp*nr_loc + j
   if (m >= g.nm_tot) return;
-  const int comp = (int)(row / g.nr_loc);
-  const int64_t j = row % g.nr_loc;
-  legF[row * g.nm_tot + m] = mapside[mapside_off(g, boff, m, j, comp)];
+  const int comp = (int)(blockIdx.y / nj);
+  const int64_t j = j0 + blockIdx.y % nj;
+  legF[(comp * g.nr_loc + j) * g.nm_tot + m] = mapside[mapside_off(g, boff, m, j, comp)];
 }
 __global__ void k_pack(const double2* __restrict__ legF, const int64_t* __restrict__ boff,
-                       double2* __restrict__ mapside, ExchGeom g) {
+                       double2* __restrict__ mapside, ExchGeom g, int64_t j0, int64_t nj) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = blockIdx.y;
   if (m >= g.nm_tot) return;
-  const int comp = (int)(row / g.nr_loc);
-  const int64_t j = row % g.nr_loc;
-  mapside[mapside_off(g, boff, m, j, comp)] = legF[row * g.nm_tot + m];
+  const int comp = (int)(blockIdx.y / nj);
+  const int64_t j = j0 + blockIdx.y % nj;
+  mapside[mapside_off(g, boff, m, j, comp)] = legF[(comp * g.nr_loc + j) * g.nm_tot + m];
 }
 
 // ---- FP64 FMA peak probe: 8 independent chains per thread, no memory traffic ----
@@ -136,10 +135,17 @@ struct hpsht_plan {
   // single-rank host-pointer calls: ring blocks pipelined against the PCIe copies of the map
   int HB = 1;
   std::vector<std::unique_ptr<RingFFT>> fftb;
-  std::vector<int64_t> blk_pix;         // first pixel of each block's (contiguous) pixel range, + end
-  std::vector<cudaEvent_t> ev_blk;
+  std::vector<int64_t> bj_lo, bj_hi;    // [block][rank]: local ring range of the block on that rank
+  std::vector<cudaEvent_t> ev_blk, ev_x, ev_f;
   cudaStream_t hstream = nullptr;       // host <-> device copies
+  cudaStream_t fstream = nullptr;       // P>1: ring FFT + pack/unpack of a block (next to the Legendre stream)
   cudaEvent_t ev_hdone = nullptr;
+  int64_t blo(int b, int t) const { return bj_lo[(size_t)b * P + t]; }
+  int64_t bhi(int b, int t) const { return bj_hi[(size_t)b * P + t]; }
+  int64_t pix_lo(int b) const { return blo(b, rank) < nr_loc ? rstart[(size_t)blo(b, rank)] : npix_loc; }
+  int64_t pix_hi(int b) const { return bhi(b, rank) < nr_loc ? rstart[(size_t)bhi(b, rank)] : npix_loc; }
+  void setup_blocks();
+  void exchange_block(bool synthesis, int ncomp, int b, cudaStream_t st);
   ncclComm_t comm = nullptr;
   std::unique_ptr<Timer> tm;
   double ms[HPSHT_NTIMES] = {0};
@@ -253,7 +259,11 @@ void hpsht_plan::ensure_stages() {
     mapside.alloc((size_t)boff[(size_t)P] * 2);
     legF.alloc((size_t)max_ncomp * nr_loc * nm_tot * 2);
     d_boff.upload(boff.data(), boff.size(), stream);
-    HP_CUDA(cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking));
+    // exchange (and the per-block FFT stream) outrank the Legendre stream: their few CTAs must not queue
+    // behind the thousands of pending CTAs of the next Legendre launch
+    int prio_lo = 0, prio_hi = 0;
+    HP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    HP_CUDA(cudaStreamCreateWithPriority(&cstream, cudaStreamNonBlocking, prio_hi));
     ev_slab.resize((size_t)K);
     for (auto& e : ev_slab) HP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ev_done.resize((size_t)K);
@@ -265,39 +275,112 @@ void hpsht_plan::ensure_stages() {
   leg.setup(lmax, mval.data(), mstart.data(), nm_loc, nr_tot, thetatot.data(), lay, max_ncomp, stream);
   HP_REQUIRE(P == 1 || leg.nslabs() == K, HPSHT_ERR_INTERNAL, "slab count mismatch");
   fft.setup(nr_loc, nphi.data(), phi0.data(), rstart.data(), nm_tot, stream);
-  if (P == 1) {
-    // Host-pointer calls move 8 B per pixel and component over PCIe, ~0.6x the time the transform
-    // itself needs at nside 4096.  With the rings cut into HB tile-aligned blocks the copy of
-    // one block overlaps the Legendre + FFT work of the next (HPSHT_HOST_BLOCKS, 1 = off).
-    const char* eb = getenv("HPSHT_HOST_BLOCKS");
-    int want = eb ? std::max(1, atoi(eb)) : 6;
-    if (!eb && npix_loc < (1 << 22)) want = 1;  // small maps: the copies are microseconds
-    std::vector<double> w((size_t)nr_loc);
-    for (int64_t i = 0; i < nr_loc; ++i) w[(size_t)i] = (double)nphi[(size_t)i];
-    HB = leg.setup_blocks(want, w.data());
-    if (HB > 1) {
-      blk_pix.assign((size_t)HB + 1, 0);
-      fftb.clear();
-      for (int b = 0; b < HB; ++b) {
-        int64_t lo, hi;
-        leg.block_slots(b, &lo, &hi);
-        blk_pix[(size_t)b] = rstart[(size_t)lo];
-        // blocks run pole -> equator, i.e. towards lower slots: block b ends where block b-1 starts
-        const int64_t pend = hi < nr_loc ? rstart[(size_t)hi] : npix_loc;
-        if (b == 0) blk_pix[(size_t)HB] = pend;
-        HP_REQUIRE(b == 0 || pend == blk_pix[(size_t)b - 1], HPSHT_ERR_INTERNAL, "ring blocks are not contiguous");
-        fftb.emplace_back(new RingFFT());
-        fftb.back()->setup(hi - lo, nphi.data() + lo, phi0.data() + lo, rstart.data() + lo, nm_tot, stream, lo,
-                           nr_loc);
-      }
-      ev_blk.resize((size_t)HB);
-      for (auto& e : ev_blk) HP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      HP_CUDA(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
-      HP_CUDA(cudaEventCreateWithFlags(&ev_hdone, cudaEventDisableTiming));
-    }
-  }
+  setup_blocks();
   HP_CUDA(cudaStreamSynchronize(stream));
   stages_ready = true;
+}
+
+
+// Host-pointer calls move 8 B per pixel and component over PCIe, ~0.4x the time the transform itself
+// needs at nside 4096.  With the ring pairs cut into HB tile-aligned blocks the copy of one block
+// overlaps the Legendre + exchange + FFT work of the others (HPSHT_HOST_BLOCKS, 1 = off).  The blocks
+// are ranges of the global pole -> equator pair list; with round-robin ring ownership every rank's
+// share of a block is a contiguous range [blo, bhi) of its local rings.
+void hpsht_plan::setup_blocks() {
+  HB = 1;
+  const char* eb = getenv("HPSHT_HOST_BLOCKS");
+  int want = eb ? std::max(1, atoi(eb)) : (P <= 2 ? 6 : 4);
+  if (!eb && npix_loc < (1 << 22)) want = 1;  // small maps: the copies are microseconds
+  if (K != 1) want = 1;
+  std::vector<double> w((size_t)nr_tot);
+  {
+    std::vector<int64_t> tot = rr_rindexes_tot(2 * nside, P);
+    for (size_t i = 0; i < tot.size(); ++i) w[i] = (double)healpix_ring(nside, tot[i]).nphi;
+  }
+  HB = leg.setup_blocks(want, w.data());
+  if (HB <= 1) return;
+  std::vector<int64_t> roff((size_t)P + 1, 0);  // first slot of every rank in thetatot order
+  for (int t = 0; t < P; ++t) roff[(size_t)t + 1] = roff[(size_t)t] + nr_of[(size_t)t];
+  bj_lo.assign((size_t)HB * P, 0);
+  bj_hi.assign((size_t)HB * P, 0);
+  bool ok = true;
+  for (int b = 0; b < HB && ok; ++b) {
+    std::vector<int64_t> lo((size_t)P, INT64_MAX), hi((size_t)P, -1), cnt((size_t)P, 0);
+    for (int64_t slot : leg.block_slot_list(b)) {
+      const int t = (int)(std::upper_bound(roff.begin(), roff.end(), slot) - roff.begin()) - 1;
+      const int64_t j = slot - roff[(size_t)t];
+      lo[(size_t)t] = std::min(lo[(size_t)t], j);
+      hi[(size_t)t] = std::max(hi[(size_t)t], j + 1);
+      ++cnt[(size_t)t];
+    }
+    for (int t = 0; t < P; ++t) {
+      if (cnt[(size_t)t] == 0) {  // no ring of this rank in the block: empty range at the running boundary
+        lo[(size_t)t] = hi[(size_t)t] = b == 0 ? nr_of[(size_t)t] : blo(b - 1, t);
+      }
+      // blocks run pole -> equator = towards lower local ring indices, without gaps
+      ok = ok && cnt[(size_t)t] == hi[(size_t)t] - lo[(size_t)t] &&
+           hi[(size_t)t] == (b == 0 ? nr_of[(size_t)t] : blo(b - 1, t));
+      bj_lo[(size_t)b * P + t] = lo[(size_t)t];
+      bj_hi[(size_t)b * P + t] = hi[(size_t)t];
+    }
+    if (b == HB - 1)
+      for (int t = 0; t < P; ++t) ok = ok && lo[(size_t)t] == 0;
+  }
+  if (!ok) {  // exotic ring order: no blocking
+    HB = leg.setup_blocks(1, w.data());
+    return;
+  }
+  fftb.clear();
+  for (int b = 0; b < HB; ++b) {
+    const int64_t lo = blo(b, rank), hi = bhi(b, rank);
+    fftb.emplace_back(new RingFFT());
+    if (hi > lo)
+      fftb.back()->setup(hi - lo, nphi.data() + lo, phi0.data() + lo, rstart.data() + lo, nm_tot, stream, lo, nr_loc);
+  }
+  for (auto* v : {&ev_blk, &ev_x, &ev_f}) {
+    v->resize((size_t)HB);
+    for (auto& e : *v) HP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  HP_CUDA(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  HP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  HP_CUDA(cudaStreamCreateWithPriority(&fstream, cudaStreamNonBlocking, prio_hi));
+  HP_CUDA(cudaEventCreateWithFlags(&ev_hdone, cudaEventDisableTiming));
+}
+
+// the leg pieces of ring block b: per peer and component one contiguous run of rows on both sides
+void hpsht_plan::exchange_block(bool synthesis, int ncomp, int b, cudaStream_t st) {
+  NcclApi& N = NcclApi::get();
+  double* A = almside.p;
+  double* B = mapside.p;
+  const int64_t mlo = blo(b, rank), mhi = bhi(b, rank);
+  HP_NCCL(N.GroupStart());
+  for (int t = 0; t < P; ++t) {
+    if (t == rank) continue;
+    for (int c = 0; c < ncomp; ++c) {
+      // alm-side: my m's x t's rings of the block ; map-side: t's m's x my rings of the block
+      const size_t na = (size_t)(bhi(b, t) - blo(b, t)) * nm_loc * 2;
+      const size_t nb = (size_t)(mhi - mlo) * nm_of[(size_t)t] * 2;
+      double* pa = A + ((size_t)aoff[(size_t)t] + ((size_t)c * nr_of[(size_t)t] + blo(b, t)) * nm_loc) * 2;
+      double* pb = B + ((size_t)boff[(size_t)t] + ((size_t)c * nr_loc + mlo) * nm_of[(size_t)t]) * 2;
+      if (synthesis) {
+        if (na) HP_NCCL(N.Send(pa, na, ncclDouble, t, comm, st));
+        if (nb) HP_NCCL(N.Recv(pb, nb, ncclDouble, t, comm, st));
+      } else {
+        if (nb) HP_NCCL(N.Send(pb, nb, ncclDouble, t, comm, st));
+        if (na) HP_NCCL(N.Recv(pa, na, ncclDouble, t, comm, st));
+      }
+    }
+  }
+  HP_NCCL(N.GroupEnd());
+  if (mhi > mlo)
+    for (int c = 0; c < ncomp; ++c) {  // own block never leaves the device
+      const size_t n = (size_t)(mhi - mlo) * nm_loc * 2;
+      double* pa = A + ((size_t)aoff[(size_t)rank] + ((size_t)c * nr_loc + mlo) * nm_loc) * 2;
+      double* pb = B + ((size_t)boff[(size_t)rank] + ((size_t)c * nr_loc + mlo) * nm_loc) * 2;
+      HP_CUDA(cudaMemcpyAsync(synthesis ? pb : pa, synthesis ? pa : pb, n * sizeof(double),
+                              cudaMemcpyDeviceToDevice, st));
+    }
 }
 
 // m-sharded <-> ring-sharded transpose of the leg array (communicate_alm2map! / communicate_map2alm!,
@@ -350,11 +433,11 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
   HP_CUDA(cudaEventRecord(e[0], stream));
   const double* d_in = in;
   double* d_out = out;
-  // pixel range [lo, hi) of ring block b (blocks are numbered pole -> equator = descending pixels)
-  auto blk_lo = [&](int b) { return blk_pix[(size_t)b]; };
-  auto blk_hi = [&](int b) { return b == 0 ? blk_pix[(size_t)HB] : blk_pix[(size_t)b - 1]; };
-  const bool pipe_out = P == 1 && HB > 1 && synthesis && !out_dev;
-  const bool pipe_in = P == 1 && HB > 1 && !synthesis && !in_dev;
+  // ring blocks are numbered pole -> equator = descending local pixels
+  auto blk_lo = [&](int b) { return pix_lo(b); };
+  auto blk_hi = [&](int b) { return pix_hi(b); };
+  const bool pipe_out = HB > 1 && synthesis && !out_dev;
+  const bool pipe_in = HB > 1 && !synthesis && !in_dev;
   if (pipe_in) {
     stage_map.ensure(map_d);
     d_in = stage_map.p;
@@ -383,25 +466,51 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
     // alm2leg (src/sht.jl:85)
     if (pipe_out) {
       // all kernels first (a pageable destination makes cudaMemcpyAsync block the host), then the copies
-      leg.alm2leg_begin(d_in, nalm_loc, legF.p, (int64_t)max_ncomp * nr_loc * nm_tot, ncomp, stream);
+      double* legdst = P == 1 ? legF.p : almside.p;
+      leg.alm2leg_begin(d_in, nalm_loc, legdst, P == 1 ? (int64_t)max_ncomp * nr_loc * nm_tot : aoff[(size_t)P],
+                        ncomp, stream);
+      if (P > 1) {
+        HP_CUDA(cudaEventRecord(ev_ready, stream));  // the stage buffers of the previous call are free again
+        HP_CUDA(cudaStreamWaitEvent(fstream, ev_ready, 0));
+      }
       for (int b = 0; b < HB; ++b) {
-        leg.alm2leg_block(b, legF.p, ncomp, stream, b == HB - 1);
+        leg.alm2leg_block(b, legdst, ncomp, stream, b == HB - 1);
         if (b == HB - 1) {
           HP_CUDA(cudaEventRecord(e[2], stream));
           HP_CUDA(cudaEventRecord(e[3], stream));
         }
-        fftb[(size_t)b]->leg2map(legF.p, d_out, npix_loc, ncomp, stream);
-        HP_CUDA(cudaEventRecord(ev_blk[(size_t)b], stream));
+        if (P == 1) {
+          fftb[(size_t)b]->leg2map(legF.p, d_out, npix_loc, ncomp, stream);
+          HP_CUDA(cudaEventRecord(ev_f[(size_t)b], stream));
+        } else {
+          // exchange of block b on the communication stream, unpack + ring FFT on the FFT stream
+          HP_CUDA(cudaEventRecord(ev_blk[(size_t)b], stream));
+          HP_CUDA(cudaStreamWaitEvent(cstream, ev_blk[(size_t)b], 0));
+          exchange_block(true, ncomp, b, cstream);
+          HP_CUDA(cudaEventRecord(ev_x[(size_t)b], cstream));
+          HP_CUDA(cudaStreamWaitEvent(fstream, ev_x[(size_t)b], 0));
+          const int64_t j0 = blo(b, rank), nj = bhi(b, rank) - j0;
+          if (nj > 0) {
+            dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nj));
+            k_unpack<<<grid, TB, 0, fstream>>>(reinterpret_cast<const double2*>(mapside.p), d_boff.p,
+                                               reinterpret_cast<double2*>(legF.p), G, j0, nj);
+            HP_CUDA(cudaGetLastError());
+            fftb[(size_t)b]->leg2map(legF.p, d_out, npix_loc, ncomp, fstream);
+            extra += 1;
+          }
+          extra += 1;
+          HP_CUDA(cudaEventRecord(ev_f[(size_t)b], fstream));
+        }
       }
       HP_CUDA(cudaEventRecord(e[4], stream));
       for (int b = 0; b < HB; ++b) {
-        HP_CUDA(cudaStreamWaitEvent(hstream, ev_blk[(size_t)b], 0));
-        for (int c = 0; c < ncomp; ++c) {
-          const size_t o = (size_t)c * npix_loc + (size_t)blk_lo(b);
-          HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, (size_t)(blk_hi(b) - blk_lo(b)) * sizeof(double),
-                                  cudaMemcpyDeviceToHost, hstream));
-        }
-        extra += 0;
+        HP_CUDA(cudaStreamWaitEvent(hstream, ev_f[(size_t)b], 0));
+        if (blk_hi(b) > blk_lo(b))
+          for (int c = 0; c < ncomp; ++c) {
+            const size_t o = (size_t)c * npix_loc + (size_t)blk_lo(b);
+            HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, (size_t)(blk_hi(b) - blk_lo(b)) * sizeof(double),
+                                    cudaMemcpyDeviceToHost, hstream));
+          }
       }
       HP_CUDA(cudaEventRecord(ev_hdone, hstream));
       HP_CUDA(cudaStreamWaitEvent(stream, ev_hdone, 0));
@@ -423,7 +532,7 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
       HP_CUDA(cudaStreamWaitEvent(stream, ev_ready, 0));
       dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nr_loc));
       k_unpack<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(mapside.p), d_boff.p,
-                                        reinterpret_cast<double2*>(legF.p), G);
+                                        reinterpret_cast<double2*>(legF.p), G, 0, nr_loc);
       HP_CUDA(cudaGetLastError());
       extra += 1 + K;
       HP_CUDA(cudaEventRecord(e[3], stream));  // exposed (non-overlapped) exchange tail + unpack
@@ -434,23 +543,52 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
       HP_CUDA(cudaEventRecord(e[4], stream));
     }
   } else if (pipe_in) {
-    // block b: host-to-device copy on the copy stream, then map2leg + leg2alm of that block; the small
-    // equator-most blocks go first so that the compute starts early
+    // block b: host-to-device copy on the copy stream, then map2leg (+ pack and exchange when P > 1) and
+    // leg2alm of that block; the small equator-most blocks go first so that the compute starts early
     leg.leg2alm_blocks_begin(ncomp, stream);
+    if (P > 1) {
+      HP_CUDA(cudaEventRecord(ev_ready, stream));
+      HP_CUDA(cudaStreamWaitEvent(fstream, ev_ready, 0));
+    }
     for (int b = HB - 1; b >= 0; --b) {
-      for (int c = 0; c < ncomp; ++c) {
-        const size_t o = (size_t)c * npix_loc + (size_t)blk_lo(b);
-        HP_CUDA(cudaMemcpyAsync(stage_map.p + o, in + o, (size_t)(blk_hi(b) - blk_lo(b)) * sizeof(double),
-                                cudaMemcpyHostToDevice, hstream));
-      }
+      if (blk_hi(b) > blk_lo(b))
+        for (int c = 0; c < ncomp; ++c) {
+          const size_t o = (size_t)c * npix_loc + (size_t)blk_lo(b);
+          HP_CUDA(cudaMemcpyAsync(stage_map.p + o, in + o, (size_t)(blk_hi(b) - blk_lo(b)) * sizeof(double),
+                                  cudaMemcpyHostToDevice, hstream));
+        }
       HP_CUDA(cudaEventRecord(ev_blk[(size_t)b], hstream));
-      HP_CUDA(cudaStreamWaitEvent(stream, ev_blk[(size_t)b], 0));
-      fftb[(size_t)b]->map2leg(d_in, npix_loc, legF.p, ncomp, stream);
-      if (b == HB - 1) {
-        HP_CUDA(cudaEventRecord(e[2], stream));
-        HP_CUDA(cudaEventRecord(e[3], stream));
+      if (P == 1) {
+        HP_CUDA(cudaStreamWaitEvent(stream, ev_blk[(size_t)b], 0));
+        fftb[(size_t)b]->map2leg(d_in, npix_loc, legF.p, ncomp, stream);
+        if (b == HB - 1) {
+          HP_CUDA(cudaEventRecord(e[2], stream));
+          HP_CUDA(cudaEventRecord(e[3], stream));
+        }
+        leg.leg2alm_block(b, legF.p, ncomp, stream, b == 0);
+      } else {
+        HP_CUDA(cudaStreamWaitEvent(fstream, ev_blk[(size_t)b], 0));
+        const int64_t j0 = blo(b, rank), nj = bhi(b, rank) - j0;
+        if (nj > 0) {
+          fftb[(size_t)b]->map2leg(d_in, npix_loc, legF.p, ncomp, fstream);
+          dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nj));
+          k_pack<<<grid, TB, 0, fstream>>>(reinterpret_cast<const double2*>(legF.p), d_boff.p,
+                                           reinterpret_cast<double2*>(mapside.p), G, j0, nj);
+          HP_CUDA(cudaGetLastError());
+          extra += 1;
+        }
+        HP_CUDA(cudaEventRecord(ev_f[(size_t)b], fstream));
+        HP_CUDA(cudaStreamWaitEvent(cstream, ev_f[(size_t)b], 0));
+        exchange_block(false, ncomp, b, cstream);
+        extra += 1;
+        HP_CUDA(cudaEventRecord(ev_x[(size_t)b], cstream));
+        HP_CUDA(cudaStreamWaitEvent(stream, ev_x[(size_t)b], 0));
+        if (b == HB - 1) {
+          HP_CUDA(cudaEventRecord(e[2], stream));
+          HP_CUDA(cudaEventRecord(e[3], stream));
+        }
+        leg.leg2alm_block(b, almside.p, ncomp, stream, b == 0);
       }
-      leg.leg2alm_block(b, legF.p, ncomp, stream, b == 0);
     }
     leg.leg2alm_blocks_end(d_out, nalm_loc, ncomp, stream);
     HP_CUDA(cudaEventRecord(e[4], stream));
@@ -464,7 +602,7 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
     } else {
       dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nr_loc));
       k_pack<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(legF.p), d_boff.p,
-                                      reinterpret_cast<double2*>(mapside.p), G);
+                                      reinterpret_cast<double2*>(mapside.p), G, 0, nr_loc);
       HP_CUDA(cudaGetLastError());
       extra += 1 + K;
       HP_CUDA(cudaEventRecord(ev_ready, stream));
@@ -498,6 +636,8 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
   HP_CUDA(cudaEventRecord(e[5], stream));
   HP_CUDA(cudaStreamSynchronize(stream));
   if (cstream) HP_CUDA(cudaStreamSynchronize(cstream));
+  if (fstream) HP_CUDA(cudaStreamSynchronize(fstream));
+  if (hstream) HP_CUDA(cudaStreamSynchronize(hstream));
   auto el = [&](int a, int b) {
     float f = 0;
     cudaEventElapsedTime(&f, e[a], e[b]);
@@ -897,6 +1037,9 @@ int hpsht_plan_destroy(hpsht_plan* plan) {
     }
     if (plan->ev_ready) cudaEventDestroy(plan->ev_ready);
     for (auto& e : plan->ev_blk) cudaEventDestroy(e);
+    for (auto& e : plan->ev_x) cudaEventDestroy(e);
+    for (auto& e : plan->ev_f) cudaEventDestroy(e);
+    if (plan->fstream) cudaStreamDestroy(plan->fstream);
     if (plan->ev_hdone) cudaEventDestroy(plan->ev_hdone);
     if (plan->hstream) cudaStreamDestroy(plan->hstream);
     if (plan->cstream) cudaStreamDestroy(plan->cstream);

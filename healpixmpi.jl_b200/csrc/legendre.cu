@@ -1887,19 +1887,21 @@ int LegendreStage::setup_blocks(int want, const double* slot_weight) {
   if (want < 1 || !adj_warp_mode()) want = 1;
   blk_pair_.push_back(0);
   // Preferred cut: multiples of the least common multiple of the four kernels' tile sizes (512 pairs
-  // with the default configurations), so that no block ends in a partly filled tile; about `want`
-  // blocks (nside 4096, want 6: 1536-pair blocks, the equator-most one -- whose copy cannot hide
-  // behind compute -- being the 512-pair remainder).  Too many blocks: merge from the pole, where
-  // blocks hold the fewest pixels.
+  // with the default configurations), so that no block ends in a partly filled tile.  The
+  // equator-most block -- whose copy cannot hide behind compute -- is a single unit (6 % of the pixels
+  // at nside 4096); the other want-1 blocks share the rest (nside 4096, want 6: 5 x 1536 + 512 pairs).
   int64_t align = 32;
   for (int t : {kSynCfgs[s0_cfg()].R * kSynCfgs[s0_cfg()].NW * 32, kSynCfgs[s2_cfg()].R * kSynCfgs[s2_cfg()].NW * 32,
                 adj_tile(0), adj_tile(2)})
     align = align / gcd_i(align, t) * t;
   if (want > 1 && np >= 2 * align) {
-    const int64_t k = std::max<int64_t>(1, (np + want * align / 2) / (want * align));
-    if (np >= 2 * k * align) align *= k;
-    for (int64_t p = align; p < np; p += align) blk_pair_.push_back((int)p);
-    while ((int)blk_pair_.size() > want) blk_pair_.erase(blk_pair_.begin() + 1);
+    // equator-most block: one unit; the rest: want-1 blocks of equal pair count (whole units)
+    const int64_t units = (np + align - 1) / align;           // last unit may be partial
+    const int64_t nb = std::min<int64_t>(want - 1, units - 1);
+    for (int64_t b = 1; b <= nb; ++b) {
+      const int64_t p = ((units - 1) * b / nb) * align;
+      if (p > blk_pair_.back() && p < np) blk_pair_.push_back((int)p);
+    }
   } else if (want > 1) {
     // small problems (tests): equal-weight blocks on warp-aligned boundaries
     std::vector<double> cum((size_t)np + 1, 0.0);
@@ -1916,19 +1918,17 @@ int LegendreStage::setup_blocks(int want, const double* slot_weight) {
     }
   }
   blk_pair_.push_back(np);
-  // a block's slots must be contiguous for the caller's copies
-  for (int b = 0; b + 1 < (int)blk_pair_.size(); ++b) {
-    int64_t lo, hi;
-    block_slots(b, &lo, &hi);
-    int64_t cnt = 0;
-    for (int p = blk_pair_[(size_t)b]; p < blk_pair_[(size_t)b + 1]; ++p) cnt += pairs_[(size_t)p].slotS >= 0 ? 2 : 1;
-    if (cnt != hi - lo) {  // exotic ring order: no blocking
-      blk_pair_.assign({0, np});
-      break;
-    }
-  }
   have0_ = have2_ = false;
   return nblocks();
+}
+
+std::vector<int64_t> LegendreStage::block_slot_list(int b) const {
+  std::vector<int64_t> v;
+  for (int p = blk_pair_[(size_t)b]; p < blk_pair_[(size_t)b + 1]; ++p) {
+    v.push_back(pairs_[(size_t)p].slotN);
+    if (pairs_[(size_t)p].slotS >= 0) v.push_back(pairs_[(size_t)p].slotS);
+  }
+  return v;
 }
 
 void LegendreStage::block_slots(int b, int64_t* slot_lo, int64_t* slot_hi) const {
@@ -1954,6 +1954,9 @@ void LegendreStage::build_block_items(int spin, const LegendreTables& T, cudaStr
   const std::vector<int64_t>& off = s2 ? T.off2 : T.off0;
   const int stile = kSynCfgs[s2 ? s2_cfg() : s0_cfg()].R * kSynCfgs[s2 ? s2_cfg() : s0_cfg()].NW * 32;
   const int atile = adj_tile(spin);
+  const int64_t total_steps = off[(size_t)nm_];
+  // enough adjoint items per block launch to fill the GPU even when a rank owns few m's
+  bgroups_ = (int)std::max<int64_t>(1, (4096 + nm_ - 1) / std::max<int64_t>(nm_, 1));
   std::vector<WorkItem> si, ai;
   std::vector<int64_t> apo;
   std::vector<int> rs, ra;
@@ -1988,13 +1991,19 @@ void LegendreStage::build_block_items(int spin, const LegendreTables& T, cudaStr
           thi = t;
         }
       if (tlo >= 0) {
-        WorkItem w;
-        w.mi = (int)mi;
-        w.p0 = pa + tlo * atile;
-        w.np = std::min(pb, pa + (thi + 1) * atile) - w.p0;
-        w.part = 0;
-        ai.push_back(w);
-        apo.push_back(off[mi]);
+        // <= G items per (m, block); item g of every block accumulates into row g of this m
+        const int nt = thi - tlo + 1;
+        const int G = std::min(bgroups_, nt);
+        for (int g = 0; g < G; ++g) {
+          const int ta = tlo + (int)((int64_t)nt * g / G), tb = tlo + (int)((int64_t)nt * (g + 1) / G);
+          WorkItem w;
+          w.mi = (int)mi;
+          w.p0 = pa + ta * atile;
+          w.np = std::min(pb, pa + tb * atile) - w.p0;
+          w.part = 0;
+          ai.push_back(w);
+          apo.push_back((int64_t)g * total_steps + off[mi]);
+        }
       }
     }
   }
@@ -2005,6 +2014,18 @@ void LegendreStage::build_block_items(int spin, const LegendreTables& T, cudaStr
   (s2 ? d_bpartoff2_ : d_bpartoff0_).upload(apo.data(), apo.size(), stream);
   (s2 ? brange_s2_ : brange_s0_) = rs;
   (s2 ? brange_a2_ : brange_a0_) = ra;
+  if (bgroups_ > 1) {  // tables for k_reduce_part over the G rows of every m
+    std::vector<int64_t> rpo((size_t)nm_ * bgroups_);
+    std::vector<int> rf((size_t)nm_), rc((size_t)nm_, bgroups_);
+    for (int64_t mi = 0; mi < nm_; ++mi) {
+      rf[(size_t)mi] = (int)(mi * bgroups_);
+      for (int g = 0; g < bgroups_; ++g) rpo[(size_t)(mi * bgroups_ + g)] = (int64_t)g * total_steps + off[(size_t)mi];
+    }
+    (s2 ? d_brpartoff2_ : d_brpartoff0_).upload(rpo.data(), rpo.size(), stream);
+    d_brfirst_.upload(rf.data(), rf.size(), stream);
+    d_brcount_.upload(rc.data(), rc.size(), stream);
+  }
+  bpart_steps_need_ = std::max(bpart_steps_need_, (size_t)(total_steps * bgroups_));
   HP_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -2031,9 +2052,9 @@ void LegendreStage::leg2alm_blocks_begin(int ncomp, cudaStream_t stream) {
   const int spin = ncomp == 1 ? 0 : 2;
   ensure_spin(spin, stream);
   HP_REQUIRE(adj_warp_mode(), HPSHT_ERR_UNSUPPORTED, "ring blocks need the single-warp adjoint kernels");
-  const size_t need = accum_steps_need_ * 4;
-  d_part_.ensure(std::max(part_steps_need_ * 4, need));
-  const int64_t total = (spin == 0 ? off0_h_ : off2_h_)[(size_t)nm_];
+  d_part_.ensure(std::max(part_steps_need_, bpart_steps_need_) * 4);
+  d_accum_.ensure(accum_steps_need_ * 4);
+  const int64_t total = (spin == 0 ? off0_h_ : off2_h_)[(size_t)nm_] * bgroups_;
   HP_CUDA(cudaMemsetAsync(d_part_.p, 0, (size_t)total * 4 * sizeof(double), stream));
   cudaEventRecord(ev0_, stream);
 }
@@ -2063,11 +2084,22 @@ void LegendreStage::leg2alm_block(int b, const double* d_leg, int ncomp, cudaStr
 void LegendreStage::leg2alm_blocks_end(double* d_alm, int64_t alm_cstride, int ncomp, cudaStream_t stream) {
   const int spin = ncomp == 1 ? 0 : 2;
   const int TB = 256;
+  const double* sums = d_part_.p;
+  if (bgroups_ > 1) {  // add the G rows of every m (fixed order) first
+    const int64_t mx = std::max<int64_t>(max_of(spin == 0 ? nstep0_h_ : nstep2_h_), 1);
+    dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
+    k_reduce_part<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p),
+                                           spin == 0 ? d_brpartoff0_.p : d_brpartoff2_.p, d_brfirst_.p,
+                                           d_brcount_.p, spin == 0 ? d_nstep0_.p : d_nstep2_.p,
+                                           spin == 0 ? d_off0_.p : d_off2_.p, reinterpret_cast<Strm*>(d_accum_.p));
+    ++launches_;
+    sums = d_accum_.p;
+  }
   if (spin == 0) {
     const int64_t mx = max_of(nstep0_h_);
     if (mx > 0) {
       dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
-      k_post_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p), d_mval_.p, d_mstart_.p,
+      k_post_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(sums), d_mval_.p, d_mstart_.p,
                                          d_nstep0_.p, d_off0_.p, d_invs0_.p, lmax_,
                                          reinterpret_cast<double2*>(d_alm));
       ++launches_;
@@ -2075,7 +2107,7 @@ void LegendreStage::leg2alm_blocks_end(double* d_alm, int64_t alm_cstride, int n
   } else {
     int64_t mx = std::max<int64_t>(max_of(nstep2_h_), 1);
     dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
-    k_post_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p), d_mval_.p, d_mstart_.p,
+    k_post_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(sums), d_mval_.p, d_mstart_.p,
                                        d_nstep2_.p, d_off2_.p, d_sig2_.p, lmax_,
                                        reinterpret_cast<double2*>(d_alm),
                                        reinterpret_cast<double2*>(d_alm) + alm_cstride);

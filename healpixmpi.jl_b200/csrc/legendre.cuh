@@ -76,12 +76,13 @@ class LegendreStage {
   void mark_main_end(cudaStream_t stream);
 
   // Ring blocks: the pole -> equator pair list cut into <= `want` contiguous ranges of about equal
-  // weight (slot_weight[slot], e.g. pixels per ring).  A block's rings occupy a contiguous slot range,
-  // so the caller can pipeline  Legendre(block) -> ring FFT(block) -> device-to-host copy(block)  and
+  // weight (slot_weight[slot], e.g. pixels per ring).  For the reference's round-robin ring order a
+  // block's rings are a contiguous local range on every rank, so the caller can pipeline  Legendre(block) -> ring FFT(block) -> device-to-host copy(block)  and
   // the reverse for the adjoint.  Call right after setup(); returns the number of blocks made.
   int setup_blocks(int want, const double* slot_weight);
   int nblocks() const { return (int)blk_pair_.size() - 1; }
-  void block_slots(int b, int64_t* slot_lo, int64_t* slot_hi) const;   // [slot_lo, slot_hi)
+  void block_slots(int b, int64_t* slot_lo, int64_t* slot_hi) const;   // hull [slot_lo, slot_hi)
+  std::vector<int64_t> block_slot_list(int b) const;                   // every ring slot of the block
   // synthesis: alm2leg_begin, then every block once in any order
   void alm2leg_block(int b, double* d_leg, int ncomp, cudaStream_t stream, bool last);
   // adjoint: leg2alm_blocks_begin, every block once (same stream), leg2alm_blocks_end
@@ -139,7 +140,10 @@ class LegendreStage {
   std::vector<int> blk_pair_;                                    // first pair of each block (+ end)
   std::vector<int> brange_s0_, brange_s2_, brange_a0_, brange_a2_;
   DevBuf<WorkItem> d_bitems_s0_, d_bitems_s2_, d_bitems_a0_, d_bitems_a2_;
-  DevBuf<int64_t> d_bpartoff0_, d_bpartoff2_;
+  DevBuf<int64_t> d_bpartoff0_, d_bpartoff2_, d_brpartoff0_, d_brpartoff2_;
+  DevBuf<int> d_brfirst_, d_brcount_;
+  int bgroups_ = 1;
+  size_t bpart_steps_need_ = 0;
   void build_block_items(int spin, const LegendreTables& T, cudaStream_t stream);
 };
 

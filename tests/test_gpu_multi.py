@@ -11,8 +11,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("host_blocks", ["1", "3"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_nccl_ranks_match_single_rank_and_oracle(nranks):
+def test_nccl_ranks_match_single_rank_and_oracle(nranks, host_blocks):
+    """host_blocks 1: one exchange per transform; 3: ring blocks pipelined (Legendre | exchange | ring FFT |
+    host copy), which the host-array API uses at large sizes."""
     import torch
 
     if torch.cuda.device_count() < nranks:
@@ -20,5 +23,6 @@ def test_nccl_ranks_match_single_rank_and_oracle(nranks):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + nranks),
            os.path.join(ROOT, "tools", "multi_gpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    env = dict(os.environ, HPSHT_HOST_BLOCKS=host_blocks)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
