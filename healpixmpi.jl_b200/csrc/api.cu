@@ -139,7 +139,8 @@ struct hpsht_plan {
   std::vector<cudaEvent_t> ev_blk, ev_x, ev_f;
   cudaStream_t hstream = nullptr;       // host <-> device copies
   cudaStream_t fstream = nullptr;       // P>1: ring FFT + pack/unpack of a block (next to the Legendre stream)
-  cudaEvent_t ev_hdone = nullptr;
+  cudaEvent_t ev_hdone = nullptr, ev_a0 = nullptr, ev_a1 = nullptr;
+  cudaStream_t pstream = nullptr;       // early post-processing of finished m's (adjoint)
   int64_t blo(int b, int t) const { return bj_lo[(size_t)b * P + t]; }
   int64_t bhi(int b, int t) const { return bj_hi[(size_t)b * P + t]; }
   int64_t pix_lo(int b) const { return blo(b, rank) < nr_loc ? rstart[(size_t)blo(b, rank)] : npix_loc; }
@@ -346,6 +347,9 @@ void hpsht_plan::setup_blocks() {
   HP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   HP_CUDA(cudaStreamCreateWithPriority(&fstream, cudaStreamNonBlocking, prio_hi));
   HP_CUDA(cudaEventCreateWithFlags(&ev_hdone, cudaEventDisableTiming));
+  HP_CUDA(cudaEventCreateWithFlags(&ev_a0, cudaEventDisableTiming));
+  HP_CUDA(cudaEventCreateWithFlags(&ev_a1, cudaEventDisableTiming));
+  HP_CUDA(cudaStreamCreateWithPriority(&pstream, cudaStreamNonBlocking, prio_hi));
 }
 
 // the leg pieces of ring block b: per peer and component one contiguous run of rows on both sides
@@ -438,9 +442,30 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
   auto blk_hi = [&](int b) { return pix_hi(b); };
   const bool pipe_out = HB > 1 && synthesis && !out_dev;
   const bool pipe_in = HB > 1 && !synthesis && !in_dev;
+  // the first synthesis block / last adjoint block (the polar one) only touches the local m's
+  // [0, mi_split): the rest of the alm copy overlaps that block's Legendre work
+  const int spin = ncomp == 1 ? 0 : 2;
+  const int mi_split = HB > 1 ? leg.block_mi_end(0, spin) : (int)nm_loc;
+  const bool split_alm = mi_split > 0 && mi_split < (int)nm_loc;
+  // alm elements of the local m's [0, mi_split) form a prefix of every component
+  const size_t a_split = split_alm ? (size_t)(mstart[(size_t)mi_split] + mval[(size_t)mi_split]) : 0;
+  const bool stream_alm_in = pipe_out && !in_dev && split_alm;
+  const bool stream_alm_out = pipe_in && !out_dev && split_alm;
   if (pipe_in) {
     stage_map.ensure(map_d);
     d_in = stage_map.p;
+  } else if (stream_alm_in) {
+    stage_alm.ensure(alm_d);
+    d_in = stage_alm.p;
+    double* dst = stage_alm.p;
+    for (int part = 0; part < 2; ++part) {
+      for (int c = 0; c < ncomp; ++c) {
+        const size_t o = ((size_t)c * nalm_loc + (part ? a_split : 0)) * 2;
+        const size_t n = (part ? (size_t)nalm_loc - a_split : a_split) * 2;
+        HP_CUDA(cudaMemcpyAsync(dst + o, in + o, n * sizeof(double), cudaMemcpyHostToDevice, hstream));
+      }
+      HP_CUDA(cudaEventRecord(part ? ev_a1 : ev_a0, hstream));
+    }
   } else if (!in_dev) {
     DevBuf<double>& sb = synthesis ? stage_alm : stage_map;
     sb.ensure(synthesis ? alm_d : map_d);
@@ -467,13 +492,22 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
     if (pipe_out) {
       // all kernels first (a pageable destination makes cudaMemcpyAsync block the host), then the copies
       double* legdst = P == 1 ? legF.p : almside.p;
-      leg.alm2leg_begin(d_in, nalm_loc, legdst, P == 1 ? (int64_t)max_ncomp * nr_loc * nm_tot : aoff[(size_t)P],
-                        ncomp, stream);
+      leg.alm2leg_zero(legdst, P == 1 ? (int64_t)max_ncomp * nr_loc * nm_tot : aoff[(size_t)P], ncomp, stream);
+      if (stream_alm_in) {
+        HP_CUDA(cudaStreamWaitEvent(stream, ev_a0, 0));
+        leg.alm2leg_prep(d_in, nalm_loc, ncomp, 0, mi_split, stream);
+      } else {
+        leg.alm2leg_prep(d_in, nalm_loc, ncomp, 0, (int)nm_loc, stream);
+      }
       if (P > 1) {
         HP_CUDA(cudaEventRecord(ev_ready, stream));  // the stage buffers of the previous call are free again
         HP_CUDA(cudaStreamWaitEvent(fstream, ev_ready, 0));
       }
       for (int b = 0; b < HB; ++b) {
+        if (b == 1 && stream_alm_in) {
+          HP_CUDA(cudaStreamWaitEvent(stream, ev_a1, 0));
+          leg.alm2leg_prep(d_in, nalm_loc, ncomp, mi_split, (int)nm_loc, stream);
+        }
         leg.alm2leg_block(b, legdst, ncomp, stream, b == HB - 1);
         if (b == HB - 1) {
           HP_CUDA(cudaEventRecord(e[2], stream));
@@ -550,6 +584,21 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
       HP_CUDA(cudaEventRecord(ev_ready, stream));
       HP_CUDA(cudaStreamWaitEvent(fstream, ev_ready, 0));
     }
+    // the local m's >= mi_split are complete before the last (polar) block starts: post-process and
+    // copy them out on the side streams while that block computes
+    auto early_alm_out = [&]() {
+      HP_CUDA(cudaEventRecord(ev_a0, stream));  // every earlier block has been accumulated
+      HP_CUDA(cudaStreamWaitEvent(pstream, ev_a0, 0));
+      leg.leg2alm_blocks_end(d_out, nalm_loc, ncomp, pstream, mi_split, (int)nm_loc);
+      HP_CUDA(cudaEventRecord(ev_a1, pstream));
+      HP_CUDA(cudaStreamWaitEvent(hstream, ev_a1, 0));
+      for (int c = 0; c < ncomp; ++c) {
+        const size_t o = ((size_t)c * nalm_loc + a_split) * 2;
+        HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, ((size_t)nalm_loc - a_split) * 2 * sizeof(double),
+                                cudaMemcpyDeviceToHost, hstream));
+      }
+      HP_CUDA(cudaEventRecord(ev_hdone, hstream));
+    };
     for (int b = HB - 1; b >= 0; --b) {
       if (blk_hi(b) > blk_lo(b))
         for (int c = 0; c < ncomp; ++c) {
@@ -565,6 +614,7 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
           HP_CUDA(cudaEventRecord(e[2], stream));
           HP_CUDA(cudaEventRecord(e[3], stream));
         }
+        if (b == 0 && stream_alm_out) early_alm_out();
         leg.leg2alm_block(b, legF.p, ncomp, stream, b == 0);
       } else {
         HP_CUDA(cudaStreamWaitEvent(fstream, ev_blk[(size_t)b], 0));
@@ -587,10 +637,11 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
           HP_CUDA(cudaEventRecord(e[2], stream));
           HP_CUDA(cudaEventRecord(e[3], stream));
         }
+        if (b == 0 && stream_alm_out) early_alm_out();
         leg.leg2alm_block(b, almside.p, ncomp, stream, b == 0);
       }
     }
-    leg.leg2alm_blocks_end(d_out, nalm_loc, ncomp, stream);
+    leg.leg2alm_blocks_end(d_out, nalm_loc, ncomp, stream, 0, stream_alm_out ? mi_split : (int)nm_loc);
     HP_CUDA(cudaEventRecord(e[4], stream));
   } else {
     // map2leg (src/sht.jl:169)
@@ -630,14 +681,22 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
     }
     HP_CUDA(cudaEventRecord(e[4], stream));
   }
-  if (!out_dev && !pipe_out)
+  if (stream_alm_out) {
+    for (int c = 0; c < ncomp; ++c) {
+      const size_t o = (size_t)c * nalm_loc * 2;
+      HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, a_split * 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    HP_CUDA(cudaStreamWaitEvent(stream, ev_hdone, 0));
+  } else if (!out_dev && !pipe_out) {
     HP_CUDA(cudaMemcpyAsync(out, d_out, (synthesis ? map_d : alm_d) * sizeof(double),
                             cudaMemcpyDeviceToHost, stream));
+  }
   HP_CUDA(cudaEventRecord(e[5], stream));
   HP_CUDA(cudaStreamSynchronize(stream));
   if (cstream) HP_CUDA(cudaStreamSynchronize(cstream));
   if (fstream) HP_CUDA(cudaStreamSynchronize(fstream));
   if (hstream) HP_CUDA(cudaStreamSynchronize(hstream));
+  if (pstream) HP_CUDA(cudaStreamSynchronize(pstream));
   auto el = [&](int a, int b) {
     float f = 0;
     cudaEventElapsedTime(&f, e[a], e[b]);
@@ -1040,6 +1099,9 @@ int hpsht_plan_destroy(hpsht_plan* plan) {
     for (auto& e : plan->ev_x) cudaEventDestroy(e);
     for (auto& e : plan->ev_f) cudaEventDestroy(e);
     if (plan->fstream) cudaStreamDestroy(plan->fstream);
+    if (plan->pstream) cudaStreamDestroy(plan->pstream);
+    if (plan->ev_a0) cudaEventDestroy(plan->ev_a0);
+    if (plan->ev_a1) cudaEventDestroy(plan->ev_a1);
     if (plan->ev_hdone) cudaEventDestroy(plan->ev_hdone);
     if (plan->hstream) cudaStreamDestroy(plan->hstream);
     if (plan->cstream) cudaStreamDestroy(plan->cstream);

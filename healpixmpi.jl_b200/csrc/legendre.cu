@@ -1512,8 +1512,8 @@ __device__ __forceinline__ double eps_lm(int64_t l, int64_t m) {
 __global__ void k_prep_s0(const double2* __restrict__ alm, const int64_t* __restrict__ mval,
                           const int64_t* __restrict__ mstart, const int64_t* __restrict__ nstep,
                           const int64_t* __restrict__ off, const double* __restrict__ invs,
-                          int64_t lmax, Strm* __restrict__ stream) {
-  const int mi = blockIdx.y;
+                          int64_t lmax, Strm* __restrict__ stream, int mi0) {
+  const int mi = mi0 + blockIdx.y;
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nstep[mi]) return;
   const int64_t m = mval[mi];
@@ -1536,8 +1536,8 @@ __global__ void k_prep_s0(const double2* __restrict__ alm, const int64_t* __rest
 __global__ void k_prep_s2(const double2* __restrict__ almE, const double2* __restrict__ almB,
                           const int64_t* __restrict__ mval, const int64_t* __restrict__ mstart,
                           const int64_t* __restrict__ nstep, const int64_t* __restrict__ off,
-                          const double* __restrict__ sig, Strm* __restrict__ stream) {
-  const int mi = blockIdx.y;
+                          const double* __restrict__ sig, Strm* __restrict__ stream, int mi0) {
+  const int mi = mi0 + blockIdx.y;
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nstep[mi]) return;
   const int64_t m = mval[mi];
@@ -1558,8 +1558,8 @@ __global__ void k_prep_s2(const double2* __restrict__ almE, const double2* __res
 __global__ void k_reduce_part(const Strm* __restrict__ part, const int64_t* __restrict__ partoff,
                               const int* __restrict__ afirst, const int* __restrict__ acount,
                               const int64_t* __restrict__ nstep, const int64_t* __restrict__ off,
-                              Strm* __restrict__ accum) {
-  const int mi = blockIdx.y;
+                              Strm* __restrict__ accum, int mi0) {
+  const int mi = mi0 + blockIdx.y;
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nstep[mi]) return;
   Strm s = {0.0, 0.0, 0.0, 0.0};
@@ -1578,8 +1578,8 @@ __global__ void k_reduce_part(const Strm* __restrict__ part, const int64_t* __re
 __global__ void k_post_s0(const Strm* __restrict__ accum, const int64_t* __restrict__ mval,
                           const int64_t* __restrict__ mstart, const int64_t* __restrict__ nstep,
                           const int64_t* __restrict__ off, const double* __restrict__ invs,
-                          int64_t lmax, double2* __restrict__ alm) {
-  const int mi = blockIdx.y;
+                          int64_t lmax, double2* __restrict__ alm, int mi0) {
+  const int mi = mi0 + blockIdx.y;
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nstep[mi]) return;
   const int64_t m = mval[mi];
@@ -1604,8 +1604,8 @@ __global__ void k_post_s0(const Strm* __restrict__ accum, const int64_t* __restr
 __global__ void k_post_s2(const Strm* __restrict__ accum, const int64_t* __restrict__ mval,
                           const int64_t* __restrict__ mstart, const int64_t* __restrict__ nstep,
                           const int64_t* __restrict__ off, const double* __restrict__ sig,
-                          int64_t lmax, double2* __restrict__ almE, double2* __restrict__ almB) {
-  const int mi = blockIdx.y;
+                          int64_t lmax, double2* __restrict__ almE, double2* __restrict__ almB, int mi0) {
+  const int mi = mi0 + blockIdx.y;
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t m = mval[mi];
   if (j == 0 && blockIdx.x == 0) {
@@ -2081,39 +2081,44 @@ void LegendreStage::leg2alm_block(int b, const double* d_leg, int ncomp, cudaStr
 }
 
 // the per-m rows of d_part_ are laid out like d_accum_ (offset off[mi]): post-process them directly
-void LegendreStage::leg2alm_blocks_end(double* d_alm, int64_t alm_cstride, int ncomp, cudaStream_t stream) {
+void LegendreStage::leg2alm_blocks_end(double* d_alm, int64_t alm_cstride, int ncomp, cudaStream_t stream,
+                                       int mi0, int mi1) {
   const int spin = ncomp == 1 ? 0 : 2;
+  if (mi1 < 0) mi1 = (int)nm_;
+  if (mi1 <= mi0) return;
   const int TB = 256;
   const double* sums = d_part_.p;
+  const int64_t mx = std::max<int64_t>(max_of(spin == 0 ? nstep0_h_ : nstep2_h_), 1);  // spin 2 also zeroes l < 2
+  dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)(mi1 - mi0));
   if (bgroups_ > 1) {  // add the G rows of every m (fixed order) first
-    const int64_t mx = std::max<int64_t>(max_of(spin == 0 ? nstep0_h_ : nstep2_h_), 1);
-    dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
     k_reduce_part<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p),
                                            spin == 0 ? d_brpartoff0_.p : d_brpartoff2_.p, d_brfirst_.p,
                                            d_brcount_.p, spin == 0 ? d_nstep0_.p : d_nstep2_.p,
-                                           spin == 0 ? d_off0_.p : d_off2_.p, reinterpret_cast<Strm*>(d_accum_.p));
+                                           spin == 0 ? d_off0_.p : d_off2_.p, reinterpret_cast<Strm*>(d_accum_.p),
+                                           mi0);
     ++launches_;
     sums = d_accum_.p;
   }
-  if (spin == 0) {
-    const int64_t mx = max_of(nstep0_h_);
-    if (mx > 0) {
-      dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
-      k_post_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(sums), d_mval_.p, d_mstart_.p,
-                                         d_nstep0_.p, d_off0_.p, d_invs0_.p, lmax_,
-                                         reinterpret_cast<double2*>(d_alm));
-      ++launches_;
-    }
-  } else {
-    int64_t mx = std::max<int64_t>(max_of(nstep2_h_), 1);
-    dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
-    k_post_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(sums), d_mval_.p, d_mstart_.p,
-                                       d_nstep2_.p, d_off2_.p, d_sig2_.p, lmax_,
-                                       reinterpret_cast<double2*>(d_alm),
-                                       reinterpret_cast<double2*>(d_alm) + alm_cstride);
-    ++launches_;
-  }
+  if (spin == 0)
+    k_post_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(sums), d_mval_.p, d_mstart_.p, d_nstep0_.p,
+                                       d_off0_.p, d_invs0_.p, lmax_, reinterpret_cast<double2*>(d_alm), mi0);
+  else
+    k_post_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(sums), d_mval_.p, d_mstart_.p, d_nstep2_.p,
+                                       d_off2_.p, d_sig2_.p, lmax_, reinterpret_cast<double2*>(d_alm),
+                                       reinterpret_cast<double2*>(d_alm) + alm_cstride, mi0);
+  ++launches_;
   HP_CUDA(cudaGetLastError());
+}
+
+// number of local m's (a prefix, m ascending) that ring block b touches at all: the others are culled
+// there (m > mlim of every pair of the block)
+int LegendreStage::block_mi_end(int b, int spin) const {
+  int ml = -1;
+  for (int p = blk_pair_[(size_t)b]; p < blk_pair_[(size_t)b + 1]; ++p)
+    ml = std::max(ml, spin == 0 ? pairs_[(size_t)p].mlim0 : pairs_[(size_t)p].mlim2);
+  int n = 0;
+  while (n < (int)nm_ && mval_[(size_t)n] <= ml) ++n;
+  return n;
 }
 
 // first item of every m-slab (items are ordered by local m index)
@@ -2233,34 +2238,40 @@ void LegendreStage::fill_params(LegParams& P, int spin, bool adjoint) const {
 }
 
 // ---- synthesis ------------------------------------------------------------------------------
-void LegendreStage::alm2leg_begin(const double* d_alm, int64_t alm_cstride, double* d_leg,
-                                  int64_t leg_elems, int ncomp, cudaStream_t stream) {
+void LegendreStage::alm2leg_zero(double* d_leg, int64_t leg_elems, int ncomp, cudaStream_t stream) {
   const int spin = ncomp == 1 ? 0 : 2;
   ensure_spin(spin, stream);
   // (m, ring) combinations beyond mlim are never visited by a CTA: their leg is exactly 0
   HP_CUDA(cudaMemsetAsync(d_leg, 0, (size_t)leg_elems * 2 * sizeof(double), stream));
+  cudaEventRecord(ev0_, stream);
+}
+
+// alm -> prepared per-step stream for the local m's [mi0, mi1)
+void LegendreStage::alm2leg_prep(const double* d_alm, int64_t alm_cstride, int ncomp, int mi0, int mi1,
+                                 cudaStream_t stream) {
+  const int spin = ncomp == 1 ? 0 : 2;
+  if (mi1 <= mi0) return;
   const int TB = 256;
-  if (spin == 0) {
-    const int64_t mx = max_of(nstep0_h_);
-    if (mx > 0) {
-      dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
-      k_prep_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(d_alm), d_mval_.p,
-                                         d_mstart_.p, d_nstep0_.p, d_off0_.p, d_invs0_.p, lmax_,
-                                         reinterpret_cast<Strm*>(d_stream0_.p));
-      ++launches_;
-    }
-  } else {
-    const int64_t mx = max_of(nstep2_h_);
-    if (mx > 0) {
-      dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
-      k_prep_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(d_alm),
-                                         reinterpret_cast<const double2*>(d_alm) + alm_cstride,
-                                         d_mval_.p, d_mstart_.p, d_nstep2_.p, d_off2_.p, d_sig2_.p,
-                                         reinterpret_cast<Strm*>(d_stream2_.p));
-      ++launches_;
-    }
-  }
+  const int64_t mx = max_of(spin == 0 ? nstep0_h_ : nstep2_h_);
+  if (mx <= 0) return;
+  dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)(mi1 - mi0));
+  if (spin == 0)
+    k_prep_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(d_alm), d_mval_.p, d_mstart_.p,
+                                       d_nstep0_.p, d_off0_.p, d_invs0_.p, lmax_,
+                                       reinterpret_cast<Strm*>(d_stream0_.p), mi0);
+  else
+    k_prep_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(d_alm),
+                                       reinterpret_cast<const double2*>(d_alm) + alm_cstride, d_mval_.p,
+                                       d_mstart_.p, d_nstep2_.p, d_off2_.p, d_sig2_.p,
+                                       reinterpret_cast<Strm*>(d_stream2_.p), mi0);
+  ++launches_;
   HP_CUDA(cudaGetLastError());
+}
+
+void LegendreStage::alm2leg_begin(const double* d_alm, int64_t alm_cstride, double* d_leg,
+                                  int64_t leg_elems, int ncomp, cudaStream_t stream) {
+  alm2leg_zero(d_leg, leg_elems, ncomp, stream);
+  alm2leg_prep(d_alm, alm_cstride, ncomp, 0, (int)nm_, stream);
   cudaEventRecord(ev0_, stream);
 }
 
@@ -2337,10 +2348,10 @@ void LegendreStage::leg2alm_end(double* d_alm, int64_t alm_cstride, int ncomp, c
       k_reduce_part<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p),
                                              d_apartoff0_.p, d_afirst0_.p, d_acount0_.p,
                                              d_nstep0_.p, d_off0_.p,
-                                             reinterpret_cast<Strm*>(d_accum_.p));
+                                             reinterpret_cast<Strm*>(d_accum_.p), 0);
       k_post_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_accum_.p), d_mval_.p,
                                          d_mstart_.p, d_nstep0_.p, d_off0_.p, d_invs0_.p, lmax_,
-                                         reinterpret_cast<double2*>(d_alm));
+                                         reinterpret_cast<double2*>(d_alm), 0);
       launches_ += 2;
     }
   } else {
@@ -2349,11 +2360,11 @@ void LegendreStage::leg2alm_end(double* d_alm, int64_t alm_cstride, int ncomp, c
     dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
     k_reduce_part<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p), d_apartoff2_.p,
                                            d_afirst2_.p, d_acount2_.p, d_nstep2_.p, d_off2_.p,
-                                           reinterpret_cast<Strm*>(d_accum_.p));
+                                           reinterpret_cast<Strm*>(d_accum_.p), 0);
     k_post_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_accum_.p), d_mval_.p,
                                        d_mstart_.p, d_nstep2_.p, d_off2_.p, d_sig2_.p, lmax_,
                                        reinterpret_cast<double2*>(d_alm),
-                                       reinterpret_cast<double2*>(d_alm) + alm_cstride);
+                                       reinterpret_cast<double2*>(d_alm) + alm_cstride, 0);
     launches_ += 2;
   }
   HP_CUDA(cudaGetLastError());

@@ -68,6 +68,10 @@ class LegendreStage {
   int nslabs() const { return (int)slab_first_mi_.size() - 1; }
   void alm2leg_begin(const double* d_alm, int64_t alm_cstride, double* d_leg, int64_t leg_elems,
                      int ncomp, cudaStream_t stream);
+  // alm2leg_begin = alm2leg_zero (clear the leg array) + alm2leg_prep over all local m's; callers that
+  // stream the alm in from the host prepare m-ranges as they arrive
+  void alm2leg_zero(double* d_leg, int64_t leg_elems, int ncomp, cudaStream_t stream);
+  void alm2leg_prep(const double* d_alm, int64_t alm_cstride, int ncomp, int mi0, int mi1, cudaStream_t stream);
   void alm2leg_slab(int slab, double* d_leg, int ncomp, cudaStream_t stream);
   void leg2alm_begin(int ncomp, cudaStream_t stream);
   void leg2alm_slab(int slab, const double* d_leg, int ncomp, cudaStream_t stream);
@@ -88,7 +92,10 @@ class LegendreStage {
   // adjoint: leg2alm_blocks_begin, every block once (same stream), leg2alm_blocks_end
   void leg2alm_blocks_begin(int ncomp, cudaStream_t stream);
   void leg2alm_block(int b, const double* d_leg, int ncomp, cudaStream_t stream, bool last);
-  void leg2alm_blocks_end(double* d_alm, int64_t alm_cstride, int ncomp, cudaStream_t stream);
+  // reduce + post-process the local m's [mi0, mi1) (default: all)
+  void leg2alm_blocks_end(double* d_alm, int64_t alm_cstride, int ncomp, cudaStream_t stream, int mi0 = 0,
+                          int mi1 = -1);
+  int block_mi_end(int b, int spin) const;
 
   double steps_culled(int spin) const { return spin ? culled2_ : culled0_; }
   double steps_dense() const { return dense_; }
