@@ -12,7 +12,7 @@ It fits one B200 (about 12 GB), so N=1 runs the same workload.
               plan's stream, max over ranks)
   e2e         ms per step through the public API (alm2map_/adjoint_alm2map_ on DAlm/DMap) with HOST
               (pinned) buffers: H2D of the inputs and D2H of the results inside the timed region
-  roofline    the dominant kernel (spin-2 Legendre recurrence) against the FP64 FMA pipe
+  roofline    the Legendre kernel with the largest share of the step against the FP64 FMA pipe
   cpu_baseline  the FP64 OpenMP CPU port (oracle/cpu_port.*; kind "port": the real reference needs
               Julia+MPI+Ducc0, absent here) timed on a bounded sample and extrapolated to the step
 
@@ -340,25 +340,41 @@ def main():
                "device_ms": e_ms, "api": "Plan.alm2map / Plan.adjoint_alm2map (hpsht_alm2map C-ABI) on pinned "
                                          "host shards, per-rank bytes"}
 
-    # ---- roofline of the dominant kernel: spin-2 Legendre recurrence (synthesis) ----
+    # ---- roofline of the dominant kernel = the Legendre kernel with the largest share of the step ----
     steps2_c, steps2_d = plan.legendre_steps(2)
     steps0_c, _ = plan.legendre_steps(0)
     import ctypes as C
     tf, secs = C.c_double(), C.c_double()
     H._lib.check(H._lib.lib().hpsht_measure_fp64_peak(C.byref(tf), C.byref(secs)))
-    kern_ms = stages.get("spin2_a2m_legendre_kernel_ms", 0.0)
-    flop = 26.0 * steps2_c  # 26 flop per (l, m, ring-pair) step for spin 2, culled count
-    achieved = flop / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else None
-    roofline = {"bound": "fp64_fma", "kernel": "k_alm2leg_s2 (spin-2 Legendre recurrence, synthesis)",
+    # 26 flop (spin 2) / 6 flop (spin 0) per (l, m, ring-pair) step, culled count
+    kernels = {
+        "k_leg2alm_s2_w (spin-2 Legendre recurrence, adjoint)": (26.0 * steps2_c, stages.get("spin2_adj_legendre_kernel_ms")),
+        "k_alm2leg_s2 (spin-2 Legendre recurrence, synthesis)": (26.0 * steps2_c, stages.get("spin2_a2m_legendre_kernel_ms")),
+        "k_leg2alm_s0_w (spin-0 Legendre recurrence, adjoint)": (6.0 * steps0_c, stages.get("spin0_adj_legendre_kernel_ms")),
+        "k_alm2leg_s0 (spin-0 Legendre recurrence, synthesis)": (6.0 * steps0_c, stages.get("spin0_a2m_legendre_kernel_ms")),
+    }
+    dom = max(kernels, key=lambda k: kernels[k][1] or 0.0)
+    flop, kern_ms = kernels[dom]
+    achieved = _tf(flop, kern_ms)
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same size, P = 1)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        ent = tj.get(dom.split(" ")[0])
+        if ent and ent.get("nside") == nside and ent.get("lmax") == lmax and world == 1:
+            traffic = ent["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "fp64_fma", "kernel": dom,
                 "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
-                "frac": (achieved / tf.value) if achieved else None, "traffic": None,
+                "frac": (achieved / tf.value) if achieved else None, "traffic": traffic,
+                "share_of_step": (kern_ms / ms_step) if kern_ms else None,
                 "peak_source": "in-repo DFMA micro-benchmark hpsht_measure_fp64_peak, same run (MEASURED_PEAKS.json "
                                "has no FP64 entry; nominal 37.2 TF at 1965 MHz)",
                 "algorithmic_flop_per_launch": flop, "kernel_ms": kern_ms,
-                "other_kernels": {
-                    "k_leg2alm_s2": _tf(26.0 * steps2_c, stages.get("spin2_adj_legendre_kernel_ms")),
-                    "k_alm2leg_s0": _tf(6.0 * steps0_c, stages.get("spin0_a2m_legendre_kernel_ms")),
-                    "k_leg2alm_s0": _tf(6.0 * steps0_c, stages.get("spin0_adj_legendre_kernel_ms"))}}
+                "other_kernels": {k.split(" ")[0]: {"tflops": _tf(*v), "frac": (_tf(*v) / tf.value) if _tf(*v) else None,
+                                                    "kernel_ms": v[1]}
+                                  for k, v in kernels.items() if k != dom}}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
