@@ -55,6 +55,13 @@ SIGNATURES = {
     "hpsht_plan_map_info": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "hpsht_alm2map": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
     "hpsht_adjoint_alm2map": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
+    "hpsht_plan_scatter_alm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
+    "hpsht_plan_gather_alm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
+    "hpsht_plan_scatter_map": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
+    "hpsht_plan_gather_map": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
+    "hpsht_plan_dot": (C.c_int, [vp, vp, vp, f64p]),
+    "hpsht_plan_almxfl": (C.c_int, [vp, vp, vp, i64, C.c_int]),
+    "hpsht_plan_alm2cl": (C.c_int, [vp, vp, vp, vp]),
     "hpsht_plan_timings": (C.c_int, [vp, f64p]),
     "hpsht_plan_launches": (C.c_int, [vp, i64p]),
     "hpsht_plan_legendre_steps": (C.c_int, [vp, C.c_int, f64p, f64p]),

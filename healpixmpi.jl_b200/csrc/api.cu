@@ -108,6 +108,18 @@ struct Timer {
 
 using namespace hpsht;
 
+// shard descriptors of one rank on the device (shards.cuh)
+struct RankAlmDesc {
+  std::vector<int64_t> mval, mstart0;
+  int64_t nalm = 0;
+  DevBuf<int64_t> d_mval, d_mstart0;
+};
+struct RankMapDesc {
+  std::vector<int64_t> rstart0, first_pix, nphi;
+  int64_t npix = 0;
+  DevBuf<int64_t> d_rstart0, d_first_pix, d_nphi;
+};
+
 struct hpsht_plan {
   int64_t nside = 0, lmax = 0;
   int rank = 0, P = 1, device = 0, max_ncomp = 1;
@@ -132,6 +144,9 @@ struct hpsht_plan {
   std::vector<int64_t> aoff, boff;  // block offsets in complex elements (max_ncomp sized)
   DevBuf<int64_t> d_boff;
   DevBuf<double> stage_alm, stage_map;  // device staging for host-pointer calls
+  RankAlmDesc own_alm;                  // shard ops (shards.cuh): this rank's descriptors, built lazily
+  RankMapDesc own_map;
+  DevBuf<double> shard_scratch;
   // single-rank host-pointer calls: ring blocks pipelined against the PCIe copies of the map
   int HB = 1;
   std::vector<std::unique_ptr<RingFFT>> fftb;
@@ -825,6 +840,8 @@ void finish_out(double* user, const double* dev, size_t n) {
 
 }  // namespace
 
+#include "shards.cuh"
+
 // =================================================================================================
 // extern "C"
 // =================================================================================================
@@ -1152,6 +1169,50 @@ int hpsht_adjoint_alm2map(hpsht_plan* plan, const double* map, double* alm, int 
   return guarded([&] {
     HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
     plan->run(false, map, alm, ncomp);
+  });
+}
+
+// ---- shard bookkeeping and algebra on the device (shards.cuh) ----
+int hpsht_plan_scatter_alm(hpsht_plan* plan, const double* global_alm, double* alm, int ncomp, int root) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    shard_exchange(*plan, 0, 0, global_alm, alm, ncomp, root);
+  });
+}
+int hpsht_plan_gather_alm(hpsht_plan* plan, const double* alm, double* global_alm, int ncomp, int root) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    shard_exchange(*plan, 0, 1, alm, global_alm, ncomp, root);
+  });
+}
+int hpsht_plan_scatter_map(hpsht_plan* plan, const double* global_map, double* map, int ncomp, int root) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    shard_exchange(*plan, 1, 0, global_map, map, ncomp, root);
+  });
+}
+int hpsht_plan_gather_map(hpsht_plan* plan, const double* map, double* global_map, int ncomp, int root) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    shard_exchange(*plan, 1, 1, map, global_map, ncomp, root);
+  });
+}
+int hpsht_plan_dot(hpsht_plan* plan, const double* alm1, const double* alm2, double* result) {
+  return guarded([&] {
+    HP_REQUIRE(plan && result, HPSHT_ERR_ARG, "null pointer");
+    *result = shard_dot(*plan, alm1, alm2);
+  });
+}
+int hpsht_plan_almxfl(hpsht_plan* plan, double* alm, const double* fl, int64_t nfl, int ncomp) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    shard_almxfl(*plan, alm, fl, nfl, ncomp);
+  });
+}
+int hpsht_plan_alm2cl(hpsht_plan* plan, const double* alm1, const double* alm2, double* cl) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    shard_alm2cl(*plan, alm1, alm2, cl);
   });
 }
 

@@ -18,6 +18,8 @@ struct NcclApi {
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclSend) Send = nullptr;
   decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -46,6 +48,8 @@ struct NcclApi {
     HP_SYM(CommDestroy, "ncclCommDestroy")
     HP_SYM(Send, "ncclSend")
     HP_SYM(Recv, "ncclRecv")
+    HP_SYM(AllReduce, "ncclAllReduce")
+    HP_SYM(Broadcast, "ncclBroadcast")
     HP_SYM(GroupStart, "ncclGroupStart")
     HP_SYM(GroupEnd, "ncclGroupEnd")
     HP_SYM(GetErrorString, "ncclGetErrorString")

@@ -125,6 +125,46 @@ class Plan:
     def adjoint_alm2map(self, mp, alm, ncomp: int, nthreads: int = 0) -> None:
         _lib.check(_lib.lib().hpsht_adjoint_alm2map(self.handle, _lib.ptr(mp), _lib.ptr(alm), ncomp, nthreads))
 
+    # ---- shards on the device: numpy arrays or torch CUDA tensors alike ----
+    def scatter_alm(self, global_alm, alm, ncomp: int, root: int = 0) -> None:
+        """MPI.Scatter!(alm, d_alm; root) (src/alm.jl:219-307): ``global_alm`` [ncomp][nalm_tot] complex is read
+        on ``root`` only (None elsewhere); ``alm`` receives this rank's shard."""
+        _lib.check(_lib.lib().hpsht_plan_scatter_alm(self.handle, _lib.ptr(global_alm) if global_alm is not None
+                                                     else None, _lib.ptr(alm), ncomp, root))
+
+    def gather_alm(self, alm, global_alm, ncomp: int, root: int = 0) -> None:
+        """MPI.Gather! (root >= 0) / MPI.Allgather! (root = -1) (src/alm.jl:313-595)."""
+        _lib.check(_lib.lib().hpsht_plan_gather_alm(self.handle, _lib.ptr(alm), _lib.ptr(global_alm)
+                                                    if global_alm is not None else None, ncomp, root))
+
+    def scatter_map(self, global_map, mp, ncomp: int, root: int = 0) -> None:
+        """MPI.Scatter!(map, d_map; root) (src/map.jl:245-330)."""
+        _lib.check(_lib.lib().hpsht_plan_scatter_map(self.handle, _lib.ptr(global_map) if global_map is not None
+                                                     else None, _lib.ptr(mp), ncomp, root))
+
+    def gather_map(self, mp, global_map, ncomp: int, root: int = 0) -> None:
+        """MPI.Gather! / MPI.Allgather! (src/map.jl:337-559)."""
+        _lib.check(_lib.lib().hpsht_plan_gather_map(self.handle, _lib.ptr(mp), _lib.ptr(global_map)
+                                                    if global_map is not None else None, ncomp, root))
+
+    def dot(self, alm1, alm2) -> float:
+        """dot(a, b) of one component each (src/alm.jl:621-660), summed over the ranks."""
+        r = C.c_double()
+        _lib.check(_lib.lib().hpsht_plan_dot(self.handle, _lib.ptr(alm1), _lib.ptr(alm2), C.byref(r)))
+        return r.value
+
+    def almxfl(self, alm, fl, ncomp: int) -> None:
+        """almxfl!(d_alm, fl) (src/alm.jl:693-713): in place, every component, fl zero-extended."""
+        fl = np.ascontiguousarray(fl, dtype=np.float64)
+        _lib.check(_lib.lib().hpsht_plan_almxfl(self.handle, _lib.ptr(alm), _lib.ptr(fl), len(fl), ncomp))
+
+    def alm2cl(self, alm1, alm2=None) -> np.ndarray:
+        """alm2cl(a[, b]) of one component each (src/cl.jl:5-38), summed over the ranks."""
+        cl = np.zeros(self.lmax + 1)
+        _lib.check(_lib.lib().hpsht_plan_alm2cl(self.handle, _lib.ptr(alm1), _lib.ptr(alm1 if alm2 is None else alm2),
+                                                _lib.ptr(cl)))
+        return cl
+
     def timings(self) -> dict:
         ms = (C.c_double * _lib.HPSHT_NTIMES)()
         _lib.check(_lib.lib().hpsht_plan_timings(self.handle, ms))

@@ -148,6 +148,31 @@ int hpsht_alm2map(hpsht_plan* plan, const double* alm, double* map, int ncomp, i
 int hpsht_adjoint_alm2map(hpsht_plan* plan, const double* map, double* alm, int ncomp,
                           int nthreads);
 
+/* ---- shards on the device: scatter / gather / algebra -------------------
+   All collective over the plan's ranks; host or device pointers.  `ncomp` components are moved
+   together ([ncomp][...] as in hpsht_alm2map).
+   Global alm: Healpix.jl Alm order, 0-based index(l, m) = m (2 lmax + 1 - m) / 2 + l, [ncomp][nalm_tot]
+   complex128, nalm_tot = (lmax+1)(lmax+2)/2.  Global map: RING order, [ncomp][12 nside^2] float64.
+
+   scatter: replaces MPI.Scatter!(alm, d_alm) / ScatterAlm! (src/alm.jl:159-186,219-307) and
+   MPI.Scatter!(map, d_map) / ScatterMap! (src/map.jl:151-212,245-330); the global array is read on
+   `root` only (may be NULL elsewhere); every rank receives exactly its shard.
+   gather: replaces MPI.Gather! / MPI.Allgather! (src/alm.jl:313-595, src/map.jl:337-559); root >= 0:
+   the global array is written on `root` only; root = -1: on every rank (Allgather!).              */
+int hpsht_plan_scatter_alm(hpsht_plan* plan, const double* global_alm, double* alm, int ncomp, int root);
+int hpsht_plan_gather_alm(hpsht_plan* plan, const double* alm, double* global_alm, int ncomp, int root);
+int hpsht_plan_scatter_map(hpsht_plan* plan, const double* global_map, double* map, int ncomp, int root);
+int hpsht_plan_gather_map(hpsht_plan* plan, const double* map, double* global_map, int ncomp, int root);
+/* dot(a, b) of one component each (nalm_loc complex128): weight 1 for m = 0 (real parts only), 2 for
+   m > 0, summed over all ranks (localdot + Allreduce, src/alm.jl:621-660).                         */
+int hpsht_plan_dot(hpsht_plan* plan, const double* alm1, const double* alm2, double* result);
+/* almxfl!: alm[l, m] *= fl[l] on every component; fl has nfl entries and is zero-extended to lmax + 1
+   (src/alm.jl:693-713).                                                                            */
+int hpsht_plan_almxfl(hpsht_plan* plan, double* alm, const double* fl, int64_t nfl, int ncomp);
+/* alm2cl of one component each: cl[l] = sum_m w_m Re(a conj b) / (2l + 1), w = 1 (m = 0) or 2, summed
+   over all ranks; cl has lmax + 1 entries (src/cl.jl:5-38).                                         */
+int hpsht_plan_alm2cl(hpsht_plan* plan, const double* alm1, const double* alm2, double* cl);
+
 /* Per-stage device times (ms, CUDA events) of the most recent fused call on this plan:
    [0] total, [1] the Legendre recurrence kernel alone, [2] whole Legendre stage (with the O(nalm)
    prep / reduce / post kernels), [3] all-to-all (+pack/unpack), [4] ring FFT, [5] H2D, [6] D2H.                                                       */

@@ -72,6 +72,43 @@ for (nside, lmax, use_oracle) in [(8, 23, True), (64, 191, True), (64, 100, True
             ok &= good
             print(f"P={world} nside={nside} lmax={lmax} spin={spin}: map rel {em:.2e} alm rel {ea:.2e} vs {tag} "
                   f"(alm2map_ {1e3*(t1-t0):.1f} ms incl. first-call setup) {'OK' if good else 'FAIL'}", flush=True)
+    # ---- device-side scatter / gather / algebra against the host restatements ----
+    if nside <= 64:
+        plan = H.Plan(nside, lmax, comm, 2)
+        rng = np.random.default_rng(77 + nside)
+        galm = rng.standard_normal((2, nalm)) + 1j * rng.standard_normal((2, nalm))
+        gmap = rng.standard_normal((2, npix))
+        d_a, d_m = H.DAlm(), H.DMap()
+        H.Scatter_([H.Alm(lmax, lmax, galm[0].copy()), H.Alm(lmax, lmax, galm[1].copy())], d_a, comm=comm)
+        H.Scatter_(H.PolarizedHealpixMap(nside, None, gmap[0].copy(), gmap[1].copy()), d_m, comm=comm)
+        a_loc = np.full((2, plan.nalm_loc), np.nan + 0j)
+        m_loc = np.full((2, plan.npix_loc), np.nan)
+        root = world - 1
+        plan.scatter_alm(galm if rank == root else None, a_loc, 2, root)
+        plan.scatter_map(gmap if rank == root else None, m_loc, 2, root)
+        good = np.array_equal(a_loc, d_a.alm.T) and np.array_equal(m_loc, d_m.pixels.T)
+        back_a = np.full_like(galm, np.nan); back_m = np.full_like(gmap, np.nan)
+        plan.gather_alm(a_loc, back_a, 2, -1)
+        plan.gather_map(m_loc, back_m, 2, -1)
+        good &= np.array_equal(back_a, galm) and np.array_equal(back_m, gmap)
+        back_a[:] = np.nan
+        plan.gather_alm(a_loc, back_a if rank == 0 else None, 2, 0)
+        if rank == 0:
+            good &= np.array_equal(back_a, galm)
+        ref = H.dot(d_a, d_a, 1, 2)
+        got = plan.dot(a_loc[0], a_loc[1])
+        good &= abs(got - ref) <= 1e-13 * abs(ref) + 1e-13
+        cl = plan.alm2cl(a_loc[0], a_loc[1])
+        l_of = np.concatenate([np.arange(m, lmax + 1) for m in range(lmax + 1)])
+        w_of = np.concatenate([np.full(lmax + 1 - m, 1.0 if m == 0 else 2.0) for m in range(lmax + 1)])
+        refcl = np.bincount(l_of, weights=w_of * (galm[0] * np.conj(galm[1])).real / (2 * l_of + 1), minlength=lmax + 1)
+        good &= np.allclose(cl, refcl, rtol=1e-12, atol=1e-14)
+        flags = comm.allgather(bool(good))
+        if rank == 0:
+            ok &= all(flags)
+            print(f"P={world} nside={nside} lmax={lmax}: device scatter/gather/allgather bit-exact, dot/alm2cl vs host "
+                  f"{'OK' if all(flags) else 'FAIL ' + str(flags)}", flush=True)
+        plan.destroy()
     H.clear_plans()
 dist.barrier()
 if rank == 0:
