@@ -79,6 +79,44 @@ function map2leg!(map::StridedMatrix{Float64}, leg::StridedArray{ComplexF64,3}, 
                 nthreads))
     leg
 end
+# Shards on the device (SURVEY 8f N1-N3).  Methods to add next to src/alm.jl:621-660, 693-713 and
+# src/cl.jl:33-38; `comp` arguments are 1-based columns of d_alm.alm as in the reference.
+function dot_fused(a, b; comp1::Integer = 1, comp2::Integer = 1, nside::Integer)
+    comm = (a.info.comm == b.info.comm) ? a.info.comm : throw(DomainError(0, "Communicators must match"))
+    p = plan_for(nside, a.info.lmax, comm)
+    res = Ref{Float64}(0.0)
+    check(ccall((:hpsht_plan_dot, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{Float64}),
+                p.handle, pointer(a.alm, (comp1 - 1) * size(a.alm, 1) + 1),
+                pointer(b.alm, (comp2 - 1) * size(b.alm, 1) + 1), res))
+    res[]
+end
+
+function almxfl_fused!(alm, fl::Vector{Float64}; nside::Integer)
+    p = plan_for(nside, alm.info.lmax, alm.info.comm)
+    check(ccall((:hpsht_plan_almxfl, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Float64}, Int64, Cint),
+                p.handle, alm.alm, fl, length(fl), size(alm.alm, 2)))
+    alm
+end
+
+function alm2cl_fused(a, b; comp1::Integer = 1, comp2::Integer = 1, nside::Integer)
+    p = plan_for(nside, a.info.lmax, a.info.comm)
+    cl = zeros(Float64, a.info.lmax + 1)
+    check(ccall((:hpsht_plan_alm2cl, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Float64}),
+                p.handle, pointer(a.alm, (comp1 - 1) * size(a.alm, 1) + 1),
+                pointer(b.alm, (comp2 - 1) * size(b.alm, 1) + 1), cl))
+    cl
+end
+
+# Scatter! / Gather! data movement for an already described shard (d_alm.info filled as in src/alm.jl:159-176):
+# global_alm is the root's Alm.alm (m-major), ignored elsewhere.
+function scatter_alm_fused!(global_alm::Union{Nothing,Vector{ComplexF64}}, d_alm; root::Integer = 0, nside::Integer)
+    p = plan_for(nside, d_alm.info.lmax, d_alm.info.comm)
+    g = global_alm === nothing ? Ptr{ComplexF64}(C_NULL) : pointer(global_alm)
+    check(ccall((:hpsht_plan_scatter_alm, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint, Cint),
+                p.handle, g, d_alm.alm, 1, root))
+    d_alm
+end
+
 end # module Sht
 
 # ------------------------------------------------------------------------------------------------
@@ -128,6 +166,44 @@ function adjoint_alm2map_fused!(d_map, d_alm; nthreads::Integer = 0)
     p = plan_for(d_map.info.nside, d_alm.info.lmax, comm; thetatot = d_map.info.thetatot, phi0 = d_map.info.phi0)
     check(ccall((:hpsht_adjoint_alm2map, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Cint),
                 p.handle, d_map.pixels, d_alm.alm, size(d_alm.alm, 2), nthreads))
+    d_alm
+end
+
+# Shards on the device (SURVEY 8f N1-N3).  Methods to add next to src/alm.jl:621-660, 693-713 and
+# src/cl.jl:33-38; `comp` arguments are 1-based columns of d_alm.alm as in the reference.
+function dot_fused(a, b; comp1::Integer = 1, comp2::Integer = 1, nside::Integer)
+    comm = (a.info.comm == b.info.comm) ? a.info.comm : throw(DomainError(0, "Communicators must match"))
+    p = plan_for(nside, a.info.lmax, comm)
+    res = Ref{Float64}(0.0)
+    check(ccall((:hpsht_plan_dot, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{Float64}),
+                p.handle, pointer(a.alm, (comp1 - 1) * size(a.alm, 1) + 1),
+                pointer(b.alm, (comp2 - 1) * size(b.alm, 1) + 1), res))
+    res[]
+end
+
+function almxfl_fused!(alm, fl::Vector{Float64}; nside::Integer)
+    p = plan_for(nside, alm.info.lmax, alm.info.comm)
+    check(ccall((:hpsht_plan_almxfl, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Float64}, Int64, Cint),
+                p.handle, alm.alm, fl, length(fl), size(alm.alm, 2)))
+    alm
+end
+
+function alm2cl_fused(a, b; comp1::Integer = 1, comp2::Integer = 1, nside::Integer)
+    p = plan_for(nside, a.info.lmax, a.info.comm)
+    cl = zeros(Float64, a.info.lmax + 1)
+    check(ccall((:hpsht_plan_alm2cl, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Float64}),
+                p.handle, pointer(a.alm, (comp1 - 1) * size(a.alm, 1) + 1),
+                pointer(b.alm, (comp2 - 1) * size(b.alm, 1) + 1), cl))
+    cl
+end
+
+# Scatter! / Gather! data movement for an already described shard (d_alm.info filled as in src/alm.jl:159-176):
+# global_alm is the root's Alm.alm (m-major), ignored elsewhere.
+function scatter_alm_fused!(global_alm::Union{Nothing,Vector{ComplexF64}}, d_alm; root::Integer = 0, nside::Integer)
+    p = plan_for(nside, d_alm.info.lmax, d_alm.info.comm)
+    g = global_alm === nothing ? Ptr{ComplexF64}(C_NULL) : pointer(global_alm)
+    check(ccall((:hpsht_plan_scatter_alm, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint, Cint),
+                p.handle, g, d_alm.alm, 1, root))
     d_alm
 end
 
