@@ -57,18 +57,31 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the thread is parked by the hardware until the phase completes or
+// the hint (ns) expires, instead of re-issuing the probe every few cycles
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
       : "memory");
+  return ok != 0;
+}
+// consumer side: the data is normally there already (the producer runs NSTAGE-1 chunks ahead)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity, 1000u)) {
+  }
+}
+// producer side: a stage is released once per chunk (microseconds); poll politely so that the spinning
+// warp does not take issue slots from the FP64 warps (ncu: 23 % of all issued instructions were the
+// SYNCS/BRA/YIELD of these loops before)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity, 4000u)) __nanosleep(200);
 }
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking probe
   uint32_t ok;
@@ -247,7 +260,7 @@ struct Pump {
   // dedicated producer: everything, blocking
   __device__ __forceinline__ void run_all() {
     for (; nissued < total; ++nissued) {
-      if (nissued >= NSTAGE) mbar_wait(&empty[nissued % NSTAGE], ((nissued / NSTAGE) - 1) & 1);
+      if (nissued >= NSTAGE) mbar_wait_relaxed(&empty[nissued % NSTAGE], ((nissued / NSTAGE) - 1) & 1);
       issue(nissued);
     }
   }
