@@ -1112,7 +1112,7 @@ struct WarpPipe {
   }
 };
 
-template <int R, int DBG = 0>
+template <int R>
 __global__ void __launch_bounds__(32, (R <= 4) ? 16 : (R <= 6 ? 12 : 1)) k_leg2alm_s0_w(LegParams P) {
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ double s_tr[16][33];
@@ -1231,26 +1231,17 @@ __global__ void __launch_bounds__(32, (R <= 4) ? 16 : (R <= 6 ? 12 : 1)) k_leg2a
                   const Coef ab = cf[h * 4 + s];
 #pragma unroll
                   for (int r = 0; r < R; ++r) {
-                    if (DBG != 2) {  // DBG == 2: timing experiment without the accumulation FMAs
-                      acc[4 * s + 0] = fma(lam2[r], er[r], acc[4 * s + 0]);
-                      acc[4 * s + 1] = fma(lam2[r], ei[r], acc[4 * s + 1]);
-                      acc[4 * s + 2] = fma(lam2[r], orr[r], acc[4 * s + 2]);
-                      acc[4 * s + 3] = fma(lam2[r], oi[r], acc[4 * s + 3]);
-                    } else if (r == 0) {
-                      acc[4 * s] += lam2[0];
-                    }
+                    acc[4 * s + 0] = fma(lam2[r], er[r], acc[4 * s + 0]);
+                    acc[4 * s + 1] = fma(lam2[r], ei[r], acc[4 * s + 1]);
+                    acc[4 * s + 2] = fma(lam2[r], orr[r], acc[4 * s + 2]);
+                    acc[4 * s + 3] = fma(lam2[r], oi[r], acc[4 * s + 3]);
                     const double t = fma(ab.a, csq[r], ab.b);
                     const double nx = fma(t, lam2[r], lam1[r]);
                     lam1[r] = lam2[r];
                     lam2[r] = nx;
                   }
                 }
-                double tot;
-                if (DBG == 1) {  // timing experiment: no cross-lane reduction
-                  tot = acc[lane & 15] + acc[(lane + 5) & 15];
-                } else {
-                  tot = warp_reduce16_smem(acc, s_tr, lane);
-                }
+                const double tot = warp_reduce16_smem(acc, s_tr, lane);
                 // 4-step group q = 2g + h: lower half-warp keeps even q, upper half odd q
                 if (lane < 16) s_res[(g * 2 + h) * 16 + lane] = tot;
               }
@@ -1514,6 +1505,245 @@ __global__ void __launch_bounds__(32, (R <= 2) ? 16 : (R <= 3 ? 12 : (R <= 4 ? 1
   }
 }
 
+// Multi-warp variant of the single-warp adjoint: the NW warps of a CTA walk NW adjacent tiles of the same m in
+// lockstep (one CTA barrier per 64-step chunk), share one coefficient stream and add their per-chunk sums in
+// shared memory before the global partial-sum update -- NW times less partial-sum and coefficient traffic.
+template <int R, int NW>
+__global__ void __launch_bounds__(NW * 32, 12 / NW) k_leg2alm_s2_mw(LegParams P) {
+  __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
+  __shared__ double s_tr_all[NW][16][33];
+  __shared__ double s_res_all[2][NW][LEG_CHUNK * 4];  // per warp: reduced sums of the current chunk (double-buffered)
+  __shared__ __align__(8) uint64_t s_full[NSTAGE];
+  constexpr int TILE = R * 32;
+
+  const WorkItem it = P.items[blockIdx.x];
+  const int mi = it.mi;
+  const int m = (int)P.mval[mi];
+  const int nl = (int)P.nstep[mi];
+  const int nsteps = (nl + LEG_GROUP - 1) / LEG_GROUP * LEG_GROUP;
+  const int nchunks = (nsteps + LEG_CHUNK - 1) / LEG_CHUNK;
+  const int ntile = (it.np + TILE - 1) / TILE;
+  const int nround = (ntile + NW - 1) / NW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+  double (*s_tr)[33] = s_tr_all[warp];
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(&s_full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const WarpPipe pipe{s_coef, s_full, P.coef + (size_t)P.off[mi] * 2, nchunks, nchunks * nround};
+  if (tid == 0)
+    for (int cn = 0; cn < NSTAGE && cn < pipe.total; ++cn) pipe.issue(cn);
+
+  const double2* leg = reinterpret_cast<const double2*>(P.leg);
+  const double kp = P.k0[mi], km = P.k1[mi];
+  const int pw = m >= 2 ? m - 2 : 2 - m;
+  const int q = m < 2 ? m : 2;
+  const int l0 = m > 2 ? m : 2;
+  const double sgnS = ((l0 + m) & 1) ? -1.0 : 1.0;
+  double* gpart = P.part + (size_t)P.partoff[blockIdx.x] * 4;
+  int cg = 0;
+
+  int buf = 0;
+  for (int round = 0; round < nround; ++round) {
+    const int tile = round * NW + warp;
+    const int tp0 = it.p0 + min(tile, ntile - 1) * TILE;
+    const int tnp = tile < ntile ? min(TILE, it.np - tile * TILE) : 0;  // 0: this warp idles through the round
+    double x[R], lp1[R], lp2[R], lm1[R], lm2[R];
+    double wpNr[R], wpNi[R], wmSr[R], wmSi[R], wmNr[R], wmNi[R], wpSr[R], wpSi[R];
+    int scp[R], scm[R];
+    bool act[R];
+    bool any_act = false;
+
+    auto load_p = [&](int r, int p) {  // inputs multiplied by d+
+      const int64_t rowoff = leg_rowoff(P, p, mi);
+      const int64_t cs = leg_cstr(P, p, mi);
+      const double2 qN = leg[leg_offN(P, p, mi) + rowoff], uN = leg[leg_offN(P, p, mi) + rowoff + cs];
+      wpNr[r] = qN.x - uN.y;
+      wpNi[r] = qN.y + uN.x;
+      const int64_t oS = leg_offS(P, p, mi);
+      if (oS >= 0) {
+        const double2 qS = leg[oS + rowoff], uS = leg[oS + rowoff + cs];
+        wmSr[r] = sgnS * (qS.x + uS.y);
+        wmSi[r] = sgnS * (qS.y - uS.x);
+      } else {
+        wmSr[r] = wmSi[r] = 0.0;
+      }
+    };
+    auto load_m = [&](int r, int p) {  // inputs multiplied by d-
+      const int64_t rowoff = leg_rowoff(P, p, mi);
+      const int64_t cs = leg_cstr(P, p, mi);
+      const double2 qN = leg[leg_offN(P, p, mi) + rowoff], uN = leg[leg_offN(P, p, mi) + rowoff + cs];
+      wmNr[r] = qN.x + uN.y;
+      wmNi[r] = qN.y - uN.x;
+      const int64_t oS = leg_offS(P, p, mi);
+      if (oS >= 0) {
+        const double2 qS = leg[oS + rowoff], uS = leg[oS + rowoff + cs];
+        wpSr[r] = sgnS * (qS.x - uS.y);
+        wpSi[r] = sgnS * (qS.y + uS.x);
+      } else {
+        wpSr[r] = wpSi[r] = 0.0;
+      }
+    };
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int pl = r * 32 + lane;
+      const bool valid = pl < tnp;
+      const int p = tp0 + (valid ? pl : 0);
+      act[r] = valid && (m <= P.mlim[p]);
+      any_act |= act[r];
+      x[r] = P.cth[p];
+      double mant;
+      int e;
+      pow_scaled(P.sth[p], pw, mant, e);
+      double fs = 1.0, fc = 1.0;
+      const double s2 = P.sh[p] * P.sh[p], c2 = P.ch[p] * P.ch[p];
+      for (int k = 0; k < q; ++k) {
+        fs *= s2;
+        fc *= c2;
+      }
+      to_scaled(kp * mant * fs, e, lp2[r], scp[r]);
+      to_scaled(km * mant * fc, e, lm2[r], scm[r]);
+      if (!act[r]) {
+        lp2[r] = lm2[r] = 0.0;
+        scp[r] = scm[r] = 0;
+      }
+      lp1[r] = lm1[r] = 0.0;
+      wpNr[r] = wpNi[r] = wmSr[r] = wmSi[r] = 0.0;
+      wmNr[r] = wmNi[r] = wpSr[r] = wpSi[r] = 0.0;
+      if (act[r] && scp[r] == 0) load_p(r, p);
+      if (act[r] && scm[r] == 0) load_m(r, p);
+    }
+    const bool warp_act = __any_sync(0xffffffffu, any_act);
+    // warp-uniform range flags, re-voted only when a scale changes (not once per group)
+    bool w_any0 = false, w_neg = false;
+    auto revote = [&]() {
+      bool mine0 = false, mineneg = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        mine0 |= act[r] && ((scp[r] == 0) || (scm[r] == 0));
+        mineneg |= (scp[r] < 0) || (scm[r] < 0);
+      }
+      w_any0 = __any_sync(0xffffffffu, mine0);
+      w_neg = __any_sync(0xffffffffu, mineneg);
+    };
+    revote();
+
+    for (int c = 0; c < nchunks; ++c, ++cg) {
+      const int st = cg % NSTAGE;
+      double* s_res = s_res_all[buf][warp];
+      // the CTA's NW*32 threads share the 256 doubles of the chunk's partial sums: NE each
+      constexpr int NE = LEG_CHUNK * 4 / (NW * 32);
+      double* gp = gpart + (size_t)c * LEG_CHUNK * 4 + tid;
+      double old[NE];
+#pragma unroll
+      for (int k = 0; k < NE; ++k) old[k] = (round > 0 || P.accumulate) ? gp[k * NW * 32] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_res[k * 32 + lane] = 0.0;  // groups that only ramp contribute 0
+      mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
+      const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
+      if (warp_act) {
+#pragma unroll 1
+        for (int g = 0; g < ng; ++g) {
+          {
+            const Coef* cf = &s_coef[st][g * LEG_GROUP];
+            if (w_any0) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                double acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                  const Coef ab = cf[h * 4 + s];
+#pragma unroll
+                  for (int r = 0; r < R; ++r) {
+                    acc[4 * s + 0] = fma(lp2[r], wpNr[r], acc[4 * s + 0]);
+                    acc[4 * s + 1] = fma(lp2[r], wpNi[r], acc[4 * s + 1]);
+                    acc[4 * s + 2] = fma(lm2[r], wmNr[r], acc[4 * s + 2]);
+                    acc[4 * s + 3] = fma(lm2[r], wmNi[r], acc[4 * s + 3]);
+                    if ((s & 1) == 0) {
+                      acc[4 * s + 0] = fma(lm2[r], wpSr[r], acc[4 * s + 0]);
+                      acc[4 * s + 1] = fma(lm2[r], wpSi[r], acc[4 * s + 1]);
+                      acc[4 * s + 2] = fma(lp2[r], wmSr[r], acc[4 * s + 2]);
+                      acc[4 * s + 3] = fma(lp2[r], wmSi[r], acc[4 * s + 3]);
+                    } else {
+                      acc[4 * s + 0] = fma(-lm2[r], wpSr[r], acc[4 * s + 0]);
+                      acc[4 * s + 1] = fma(-lm2[r], wpSi[r], acc[4 * s + 1]);
+                      acc[4 * s + 2] = fma(-lp2[r], wmSr[r], acc[4 * s + 2]);
+                      acc[4 * s + 3] = fma(-lp2[r], wmSi[r], acc[4 * s + 3]);
+                    }
+                    const double tp = fma(x[r], ab.a, ab.b);
+                    const double tm = fma(x[r], ab.a, -ab.b);
+                    const double np_ = fma(tp, lp2[r], -lp1[r]);
+                    const double nm_ = fma(tm, lm2[r], -lm1[r]);
+                    lp1[r] = lp2[r];
+                    lp2[r] = np_;
+                    lm1[r] = lm2[r];
+                    lm2[r] = nm_;
+                  }
+                }
+                const double tot = warp_reduce16_smem(acc, s_tr, lane);
+                if (lane < 16) s_res[(g * 2 + h) * 16 + lane] = tot;
+              }
+            } else {
+#pragma unroll
+              for (int s = 0; s < LEG_GROUP; ++s) {
+                const Coef ab = cf[s];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                  const double tp = fma(x[r], ab.a, ab.b);
+                  const double tm = fma(x[r], ab.a, -ab.b);
+                  const double np_ = fma(tp, lp2[r], -lp1[r]);
+                  const double nm_ = fma(tm, lm2[r], -lm1[r]);
+                  lp1[r] = lp2[r];
+                  lp2[r] = np_;
+                  lm1[r] = lm2[r];
+                  lm2[r] = nm_;
+                }
+              }
+            }
+            if (w_neg) {
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const int p = tp0 + r * 32 + lane;
+                if (scp[r] < 0 && is_big(lp2[r])) {
+                  lp1[r] *= SC_DOWN;
+                  lp2[r] *= SC_DOWN;
+                  scp[r] += 1;
+                  if (scp[r] == 0) load_p(r, p);
+                }
+                if (scm[r] < 0 && is_big(lm2[r])) {
+                  lm1[r] *= SC_DOWN;
+                  lm2[r] *= SC_DOWN;
+                  scm[r] += 1;
+                  if (scm[r] == 0) load_m(r, p);
+                }
+              }
+              revote();  // scales changed: refresh the warp-uniform flags
+            }
+          }
+        }
+      }
+      __syncthreads();  // every warp's sums of this chunk are in shared memory; the coefficient stage is free
+      if (tid == 0 && cg + NSTAGE < pipe.total) {
+        fence_proxy_async();  // the stage was read through the generic proxy
+        pipe.issue(cg + NSTAGE);
+      }
+#pragma unroll
+      for (int k = 0; k < NE; ++k) {
+        double v = old[k];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += s_res_all[buf][w][k * NW * 32 + tid];
+        gp[k * NW * 32] = v;
+      }
+      buf ^= 1;  // the other buffer was last read before the barrier above
+    }
+  }
+}
+
 // ================================================================================================
 // prep / post kernels (HBM-bound, O(nalm))
 // ================================================================================================
@@ -1696,13 +1926,16 @@ namespace {
 // kernel configurations
 // synthesis kernel variants (R pairs per thread, NW consumer warps); selectable at run time for tuning
 struct SynCfg { int R, NW; };
-static const SynCfg kSynCfgs[] = {{2, 4}, {4, 4}, {2, 8}, {3, 4}, {4, 2}, {4, 1}, {8, 1}, {2, 1}, {3, 1}, {2, 2}, {6, 4}, {8, 4}, {8, 2}};
+// tile shapes instantiated for the multi-warp kernels: R ring pairs per thread x NW consumer warps
+// (round-1 tuning, tools/tune.py: larger R, fewer warps and single-warp synthesis CTAs were all slower)
+static const SynCfg kSynCfgs[] = {{2, 4}, {4, 4}, {2, 8}, {3, 4}};
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
-static int s0_cfg() { return env_int("HPSHT_S0_CFG", 1); }  // default <4,4>: 512 pairs / tile
-static int s2_cfg() { return env_int("HPSHT_S2_CFG", 0); }  // default <2,4>: 256 pairs / tile
+static int cfg_clip(int i) { return i < 0 ? 0 : (i > 3 ? 3 : i); }
+static int s0_cfg() { return cfg_clip(env_int("HPSHT_S0_CFG", 1)); }  // default <4,4>: 512 pairs / tile
+static int s2_cfg() { return cfg_clip(env_int("HPSHT_S2_CFG", 0)); }  // default <2,4>: 256 pairs / tile
 static int env_syn_prod() { return env_int("HPSHT_SYN_PROD", 1); }  // 1 dedicated producer warp, 2 polling
 static int env_adj_prod() { return env_int("HPSHT_ADJ_PROD", 2); }
 #define HP_LAUNCH_P(KERNEL, PROD, cfgidx, nitems, stream, P)                                          \
@@ -1712,16 +1945,7 @@ static int env_adj_prod() { return env_int("HPSHT_ADJ_PROD", 2); }
       case 0: KERNEL<2, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;            \
       case 1: KERNEL<4, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;            \
       case 2: KERNEL<2, 8, PROD><<<(unsigned)(nitems), 8 * 32 + xw, 0, stream>>>(P); break;            \
-      case 3: KERNEL<3, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;            \
-      case 4: KERNEL<4, 2, PROD><<<(unsigned)(nitems), 2 * 32 + xw, 0, stream>>>(P); break;            \
-      case 5: KERNEL<4, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
-      case 6: KERNEL<8, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
-      case 7: KERNEL<2, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
-      case 8: KERNEL<3, 1, PROD><<<(unsigned)(nitems), 1 * 32 + xw, 0, stream>>>(P); break;            \
-      case 9: KERNEL<2, 2, PROD><<<(unsigned)(nitems), 2 * 32 + xw, 0, stream>>>(P); break;            \
-      case 10: KERNEL<6, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;           \
-      case 11: KERNEL<8, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;           \
-      default: KERNEL<8, 2, PROD><<<(unsigned)(nitems), 2 * 32 + xw, 0, stream>>>(P); break;           \
+      default: KERNEL<3, 4, PROD><<<(unsigned)(nitems), 4 * 32 + xw, 0, stream>>>(P); break;           \
     }                                                                                                  \
   } while (0)
 #define HP_LAUNCH(KERNEL, prod, cfgidx, nitems, stream, P)                                            \
@@ -1729,8 +1953,8 @@ static int env_adj_prod() { return env_int("HPSHT_ADJ_PROD", 2); }
     if ((prod) == 1) HP_LAUNCH_P(KERNEL, 1, cfgidx, nitems, stream, P);                                \
     else HP_LAUNCH_P(KERNEL, 2, cfgidx, nitems, stream, P);                                            \
   } while (0)
-static int a0_cfg() { return env_int("HPSHT_A0_CFG", 1); }  // block-mode adjoint <4,4>
-static int a2_cfg() { return env_int("HPSHT_A2_CFG", 0); }  // block-mode adjoint <2,4>
+static int a0_cfg() { return cfg_clip(env_int("HPSHT_A0_CFG", 1)); }  // block-mode adjoint <4,4>
+static int a2_cfg() { return cfg_clip(env_int("HPSHT_A2_CFG", 0)); }  // block-mode adjoint <2,4>
 // adjoint kernel family: 1 = single-warp CTAs (k_leg2alm_*_w), 0 = 4-warp CTAs with a chunk barrier
 static int adj_warp_mode() { return env_int("HPSHT_ADJ_WARP", 1); }
 static int a0w_R() { return env_int("HPSHT_A0W_R", 8); }
@@ -1744,6 +1968,14 @@ static int a2w_R() { return env_int("HPSHT_A2W_R", 4); }
       case 6: KERNEL<6><<<(unsigned)(nitems), 32, 0, stream>>>(P); break;                              \
       default: KERNEL<8><<<(unsigned)(nitems), 32, 0, stream>>>(P); break;                             \
     }                                                                                                  \
+  } while (0)
+// warps per CTA of the spin-2 adjoint: 1 = k_leg2alm_s2_w (default, fastest), 2 / 4 = k_leg2alm_s2_mw<4, NW>:
+// NW times less partial-sum DRAM traffic for 3 % (NW = 2) / 11 % (NW = 4) more time (nside 2048, round 1)
+static int adj_nw() { return env_int("HPSHT_ADJ_NW", 1); }
+#define HP_LAUNCH_MW(KERNEL, NWval, nitems, stream, P)                                                 \
+  do {                                                                                                 \
+    if ((NWval) == 2) KERNEL<4, 2><<<(unsigned)(nitems), 64, 0, stream>>>(P);                          \
+    else KERNEL<4, 4><<<(unsigned)(nitems), 128, 0, stream>>>(P);                                      \
   } while (0)
 static int adj_tile(int spin) {
   if (adj_warp_mode()) return 32 * (spin == 0 ? a0w_R() : a2w_R());
@@ -2086,7 +2318,12 @@ void LegendreStage::leg2alm_block(int b, const double* d_leg, int ncomp, cudaStr
     if (spin == 0)
       HP_LAUNCH_W(k_leg2alm_s0_w, a0w_R(), count, stream, P);
     else
-      HP_LAUNCH_W(k_leg2alm_s2_w, a2w_R(), count, stream, P);
+      {
+        if (adj_nw() > 1 && a2w_R() == 4)
+          HP_LAUNCH_MW(k_leg2alm_s2_mw, adj_nw(), count, stream, P);
+        else
+          HP_LAUNCH_W(k_leg2alm_s2_w, a2w_R(), count, stream, P);
+      }
     ++launches_;
     HP_CUDA(cudaGetLastError());
   }
@@ -2339,7 +2576,12 @@ void LegendreStage::leg2alm_slab(int slab, const double* d_leg, int ncomp, cudaS
         HP_LAUNCH(k_leg2alm_s0, env_adj_prod(), a0_cfg(), count, stream, P);
     } else {
       if (adj_warp_mode())
-        HP_LAUNCH_W(k_leg2alm_s2_w, a2w_R(), count, stream, P);
+        {
+        if (adj_nw() > 1 && a2w_R() == 4)
+          HP_LAUNCH_MW(k_leg2alm_s2_mw, adj_nw(), count, stream, P);
+        else
+          HP_LAUNCH_W(k_leg2alm_s2_w, a2w_R(), count, stream, P);
+      }
       else
         HP_LAUNCH(k_leg2alm_s2, env_adj_prod(), a2_cfg(), count, stream, P);
     }

@@ -15,7 +15,7 @@ for spec in sys.argv[3:]:
     if kind.endswith("w"):  # single-warp adjoint kernels: a0w:<R>
         os.environ["HPSHT_ADJ_WARP"] = "1"
         os.environ["HPSHT_A%dW_R" % spin] = parts[1]
-        os.environ["HPSHT_DBG"] = parts[2] if len(parts) > 2 else "0"
+        os.environ["HPSHT_ADJ_NW"] = parts[2] if len(parts) > 2 else "1"   # a2w:<R>:<warps per CTA>
     else:
         if adj:
             os.environ["HPSHT_ADJ_WARP"] = "0"
