@@ -449,6 +449,48 @@ def test_large_size_properties(H, O):
         plan.destroy()
 
 
+def test_headline_size_properties(H, O):
+    """BASELINE headline size (nside 4096, lmax 8191), both spins, through size-independent properties:
+    the host-pointer call (ring blocks pipelined against the PCIe copies, alm streamed in two m-ranges) must
+    reproduce the device-resident unblocked call bit for bit in synthesis and to summation order in the
+    adjoint (1e-13), and the pair must satisfy the adjointness identity under the localdot weights."""
+    import torch
+
+    import healpixmpi_jl_b200 as Hm
+
+    nside, lmax = 4096, 8191
+    plan = Hm.Plan(nside, lmax, Hm.COMM_SELF, 2)
+    w = torch.from_numpy(np.concatenate([np.full(lmax + 1 - m, 1.0 if m == 0 else 2.0) for m in range(lmax + 1)])).cuda()
+    for ncomp in (1, 2):
+        g = torch.Generator(device="cuda").manual_seed(40 + ncomp)
+        a = torch.randn((ncomp, plan.nalm_loc, 2), dtype=torch.float64, device="cuda", generator=g)
+        a[:, :lmax + 1, 1] = 0  # real a_l0
+        f = torch.randn((ncomp, plan.npix_loc), dtype=torch.float64, device="cuda", generator=g)
+        m_dev = torch.zeros_like(f)
+        plan.alm2map(a, m_dev, ncomp)
+        launches_dev = plan.launches()
+        a_host = a.cpu().numpy()
+        m_host = np.zeros((ncomp, plan.npix_loc))
+        plan.alm2map(a_host, m_host, ncomp)
+        assert plan.launches() > launches_dev  # the blocked path ran
+        assert np.array_equal(m_host, m_dev.cpu().numpy())
+        out_dev = torch.zeros_like(a)
+        plan.adjoint_alm2map(f, out_dev, ncomp)
+        out_host = np.zeros((ncomp, plan.nalm_loc, 2))
+        plan.adjoint_alm2map(f.cpu().numpy(), out_host, ncomp)
+        d = torch.from_numpy(out_host).cuda() - out_dev
+        # two summation orders over 16383 rings of random data: ~ sqrt(nrings) * eps
+        err = float(torch.linalg.norm(d) / torch.linalg.norm(out_dev))
+        assert err < 1e-13, err
+        lhs = float(torch.sum(f * m_dev))
+        rhs = float(torch.sum(w[None, :, None] * out_dev * a))
+        scale = float(torch.linalg.norm(f) * torch.linalg.norm(m_dev))
+        assert abs(lhs - rhs) <= 1e-12 * scale, (lhs, rhs, scale)
+        del a, f, m_dev, out_dev, d
+    plan.destroy()
+    torch.cuda.empty_cache()
+
+
 def test_config5_nside8192_adjointness(H, O):
     """BASELINE config 5 (spin-0 adjoint at nside 8192, lmax 16383; rings of up to 32768 pixels take the
     long-ring FFT path): the adjointness identity <f, Y a> = <Y^T f, a>_w at full size, device resident."""
