@@ -85,6 +85,30 @@ __device__ __forceinline__ void build_roots(double2* hi, double2* lo, int n, dou
   }
 }
 
+// exp(i m phi0) for all m of one ring.  HEALPix rings have phi0 = pq * pi / n with pq = 0 or 1, i.e. the
+// phases are 2n-th roots of unity: omega_2n^t = W(t >> 1) * (t odd ? exp(i pi / n) : 1) from the n-th root
+// table the CTA holds anyway -- ~10 flops instead of a double-precision sincos per element.  Rings whose
+// phi0 is not such a multiple (pq < 0; custom geometries) take the general path.
+struct Phase {
+  double phi0;
+  int pq;
+  unsigned n2;
+  double2 c1;
+  Roots W;
+  __device__ __forceinline__ Phase(const RingDesc& d, const Roots& w) : phi0(d.phi0), pq(d.pq), n2(2u * (unsigned)d.nphi), W(w) {
+    double s, c;
+    sincospi(1.0 / (double)d.nphi, &s, &c);
+    c1 = make_double2(c, s);
+  }
+  __device__ __forceinline__ double2 operator()(int m) const {
+    if (pq < 0) return phase(m, phi0);
+    if (pq == 0) return make_double2(1.0, 0.0);
+    const unsigned t = (unsigned)(((unsigned long long)(unsigned)m * (unsigned)pq) % n2);
+    const double2 w = W((int)(t >> 1));
+    return (t & 1u) ? cmul(w, c1) : w;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // in-place power-of-two FFT passes over shared memory (all threads of the CTA participate)
 //   DIF: natural order in, bit-reversed out.  DIT: bit-reversed in, natural out.
@@ -273,6 +297,8 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
 
   build_roots(S.hi, S.lo, n, 1.0, tid, nt);
   build_roots(S.hi2, S.lo2, d.M ? d.M : d.r, -1.0, tid, nt);
+  __syncthreads();  // the phases below come from the root table
+  const Phase PH(d, W);
 
   // ---- phase shift + alias fold: X[k], k = 0..N ----
   {
@@ -284,17 +310,17 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
       if (k == 0) {
         if (g == 0) ar = row[0].x;  // c_0 = 1, only Re(leg[0]) enters
         for (long long m = (long long)(g + 1) * n; m <= mmax; m += (long long)G * n) {
-          const double2 t = cmul(row[m], phase((int)m, d.phi0));
+          const double2 t = cmul(row[m], PH((int)m));
           ar += 2.0 * t.x;
         }
       } else {
         for (long long m = k + (long long)g * n; m <= mmax; m += (long long)G * n) {
-          const double2 t = cmul(row[m], phase((int)m, d.phi0));
+          const double2 t = cmul(row[m], PH((int)m));
           ar += t.x;
           ai += t.y;
         }
         for (long long m = (long long)(g + 1) * n - k; m <= mmax; m += (long long)G * n) {
-          const double2 t = cmul(row[m], phase((int)m, d.phi0));
+          const double2 t = cmul(row[m], PH((int)m));
           ar += t.x;
           ai -= t.y;
         }
@@ -468,10 +494,11 @@ __global__ void __launch_bounds__(1024) k_map2leg(const RingDesc* __restrict__ d
   }
   __syncthreads();
   // ---- un-alias + phase shift: leg[m] = exp(-i m phi0) Xt[m mod n] ----
+  const Phase PH(d, W);
   for (int m = tid; m <= mmax; m += nt) {
     const int k = m % n;
     const double2 v = (k <= N) ? S.A[k] : cconj(S.A[n - k]);
-    row[m] = cmulc(v, phase(m, d.phi0));
+    row[m] = cmulc(v, PH(m));
   }
 }
 
@@ -528,22 +555,22 @@ constexpr int LONG_MH = 8192;
 
 // X[k] of the alias-folded, phase-shifted spectrum, evaluated straight from the leg row (k in [0, n/2])
 __device__ __forceinline__ double2 fold_eval(const double2* __restrict__ row, int k, int n, int mmax,
-                                             double phi0) {
+                                             const Phase& PH) {
   double ar = 0.0, ai = 0.0;
   if (k == 0) {
     ar = row[0].x;
     for (long long m = n; m <= mmax; m += n) {
-      const double2 t = cmul(row[m], phase((int)m, phi0));
+      const double2 t = cmul(row[m], PH((int)m));
       ar += 2.0 * t.x;
     }
   } else {
     for (long long m = k; m <= mmax; m += n) {
-      const double2 t = cmul(row[m], phase((int)m, phi0));
+      const double2 t = cmul(row[m], PH((int)m));
       ar += t.x;
       ai += t.y;
     }
     for (long long m = (long long)n - k; m <= mmax; m += n) {
-      const double2 t = cmul(row[m], phase((int)m, phi0));
+      const double2 t = cmul(row[m], PH((int)m));
       ar += t.x;
       ai -= t.y;
     }
@@ -553,17 +580,17 @@ __device__ __forceinline__ double2 fold_eval(const double2* __restrict__ row, in
 
 // Zc[k], 0 <= k < N = 2r, from the folded spectrum
 __device__ __forceinline__ double2 zc_eval(const double2* __restrict__ row, int k, int r, int n, int mmax,
-                                           double phi0, const Roots& W) {
+                                           const Phase& PH, const Roots& W) {
   const int N = 2 * r;
   if (k == 0) {
-    const double x0 = fold_eval(row, 0, n, mmax, phi0).x, xn = fold_eval(row, N, n, mmax, phi0).x;
+    const double x0 = fold_eval(row, 0, n, mmax, PH).x, xn = fold_eval(row, N, n, mmax, PH).x;
     return make_double2(x0 + xn, x0 - xn);
   }
   if (k == r) {
-    const double2 a = fold_eval(row, r, n, mmax, phi0);
+    const double2 a = fold_eval(row, r, n, mmax, PH);
     return make_double2(2.0 * a.x, -2.0 * a.y);
   }
-  const double2 A = fold_eval(row, k, n, mmax, phi0), B = cconj(fold_eval(row, N - k, n, mmax, phi0));
+  const double2 A = fold_eval(row, k, n, mmax, PH), B = cconj(fold_eval(row, N - k, n, mmax, PH));
   const double2 Pp = cadd(A, B);
   const double2 D = cmul(csub(A, B), W(k));
   return make_double2(Pp.x - D.y, Pp.y + D.x);  // P + i w^k (A - B)
@@ -607,10 +634,11 @@ __global__ void __launch_bounds__(1024) k_long_pre(const RingDesc* __restrict__ 
   const Roots W{S.hi, S.lo};
   build_roots(S.hi, S.lo, n, 1.0, tid, nt);
   __syncthreads();
+  const Phase PH(d, W);
   double2* uv = scratch + (int64_t)comp * scratch_cstride + d.soff;
   for (int k = tid; k < r; k += nt) {
-    const double2 a = zc_eval(row, k, r, n, mmax, d.phi0, W);
-    const double2 b = zc_eval(row, k + r, r, n, mmax, d.phi0, W);
+    const double2 a = zc_eval(row, k, r, n, mmax, PH, W);
+    const double2 b = zc_eval(row, k + r, r, n, mmax, PH, W);
     uv[k] = cadd(a, b);
     uv[k + r] = cmul(csub(a, b), W(2 * k));
   }
@@ -720,6 +748,7 @@ __global__ void __launch_bounds__(1024) k_long_post(const RingDesc* __restrict__
   const Roots W{S.hi, S.lo};
   build_roots(S.hi, S.lo, n, 1.0, tid, nt);
   __syncthreads();
+  const Phase PH(d, W);
   const double2* uv = scratch + (int64_t)comp * scratch_cstride + d.soff;
   auto Z = [&](int k) -> double2 {  // k in [0, N]; Z[N] = Z[0]
     if (k >= N) k -= N;
@@ -738,7 +767,7 @@ __global__ void __launch_bounds__(1024) k_long_post(const RingDesc* __restrict__
     const double sg = (k == N) ? -1.0 : 1.0;
     const double2 X = make_double2(Pp.x + sg * 0.5 * D.y, Pp.y - sg * 0.5 * D.x);  // P - i/2 conj(w^k)(A-B)
     const double2 v = up ? cconj(X) : X;
-    row[m] = cmulc(v, phase(m, d.phi0));
+    row[m] = cmulc(v, PH(m));
   }
 }
 
@@ -833,6 +862,15 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     RingDesc d;
     d.pixoff = ringstart[i];
     d.phi0 = phi0[i];
+    {  // phi0 = pq * pi / n with an integer pq (every HEALPix ring: 0 or 1)?  The table path evaluates the
+       // phases of the exact rational; the caller's double phi0 is within 2^-53 of it, so the two differ by
+       // <= mmax * phi0 * 1.1e-16 rad: accepted up to 2e-15 (short polar rings keep the general path).
+      const double qd = phi0[i] * (double)n / 3.14159265358979323846;
+      const double qr = std::nearbyint(qd);
+      const bool rational = qr >= 0.0 && qr < 2.0 * (double)n && std::fabs(qd - qr) <= 4e-15 * std::max(1.0, qr);
+      d.pq = (rational && (double)(nm - 1) * std::fabs(phi0[i]) <= 16.0) ? (int)qr : -1;
+      if (getenv("HPSHT_FFT_GENERAL_PHASE")) d.pq = -1;
+    }
     d.ir = (int)(slot0 + i);
     d.nphi = (int)n;
     d.r = (int)(n / 4);

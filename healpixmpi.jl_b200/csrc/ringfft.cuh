@@ -19,6 +19,7 @@ struct RingDesc {
   int64_t pixoff;   // 0-based offset of the ring's first pixel in one map component
   int64_t hoff;     // offset (complex elements) of the ring's chirp spectrum, -1 for power-of-two r
   double phi0;
+  int pq;           // phi0 = pq * pi / nphi (phases from the root table), or -1: general phi0
   int ir;           // ring slot in the leg array
   int nphi;         // ring length n = 4 r
   int r;
