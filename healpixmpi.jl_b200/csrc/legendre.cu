@@ -2415,6 +2415,9 @@ void LegendreStage::ensure_spin(int spin, cudaStream_t stream) {
     off0_h_ = T.off0;
     srange_s0_ = slab_item_ranges(items_s0_, slab_first_mi_);
     srange_a0_ = slab_item_ranges(items_a0_, slab_first_mi_);
+    direct0_ = true;  // one item per m whose partial row sits at off[mi]: the post kernel reads it in place
+    for (int64_t i = 0; i < nm_; ++i)
+      direct0_ = direct0_ && acount0_[(size_t)i] == 1 && apartoff0_[(size_t)afirst0_[(size_t)i]] == T.off0[(size_t)i];
     have0_ = true;
   } else {
     d_nstep2_.upload(T.nstep2.data(), T.nstep2.size(), stream);
@@ -2441,6 +2444,9 @@ void LegendreStage::ensure_spin(int spin, cudaStream_t stream) {
     off2_h_ = T.off2;
     srange_s2_ = slab_item_ranges(items_s2_, slab_first_mi_);
     srange_a2_ = slab_item_ranges(items_a2_, slab_first_mi_);
+    direct2_ = true;
+    for (int64_t i = 0; i < nm_; ++i)
+      direct2_ = direct2_ && acount2_[(size_t)i] == 1 && apartoff2_[(size_t)afirst2_[(size_t)i]] == T.off2[(size_t)i];
     have2_ = true;
   }
   if (nblocks() > 1) build_block_items(spin, T, stream);
@@ -2596,32 +2602,27 @@ void LegendreStage::mark_main_end(cudaStream_t stream) { cudaEventRecord(ev1_, s
 void LegendreStage::leg2alm_end(double* d_alm, int64_t alm_cstride, int ncomp, cudaStream_t stream) {
   const int spin = ncomp == 1 ? 0 : 2;
   const int TB = 256;
-  if (spin == 0) {
-    const int64_t mx = max_of(nstep0_h_);
-    if (mx > 0) {
-      dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
-      k_reduce_part<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p),
-                                             d_apartoff0_.p, d_afirst0_.p, d_acount0_.p,
-                                             d_nstep0_.p, d_off0_.p,
-                                             reinterpret_cast<Strm*>(d_accum_.p), 0);
-      k_post_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_accum_.p), d_mval_.p,
-                                         d_mstart_.p, d_nstep0_.p, d_off0_.p, d_invs0_.p, lmax_,
-                                         reinterpret_cast<double2*>(d_alm), 0);
-      launches_ += 2;
-    }
-  } else {
-    int64_t mx = max_of(nstep2_h_);
-    mx = std::max<int64_t>(mx, 1);  // the post kernel also zeroes l < 2
-    dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
-    k_reduce_part<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p), d_apartoff2_.p,
-                                           d_afirst2_.p, d_acount2_.p, d_nstep2_.p, d_off2_.p,
+  const int64_t mx = std::max<int64_t>(max_of(spin == 0 ? nstep0_h_ : nstep2_h_), 1);  // spin 2 also zeroes l < 2
+  dim3 grid((unsigned)((mx + TB - 1) / TB), (unsigned)nm_);
+  const double* sums = d_part_.p;
+  if (!(spin == 0 ? direct0_ : direct2_)) {  // several items per m: add their partial rows in fixed order
+    k_reduce_part<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_part_.p),
+                                           spin == 0 ? d_apartoff0_.p : d_apartoff2_.p,
+                                           spin == 0 ? d_afirst0_.p : d_afirst2_.p,
+                                           spin == 0 ? d_acount0_.p : d_acount2_.p,
+                                           spin == 0 ? d_nstep0_.p : d_nstep2_.p, spin == 0 ? d_off0_.p : d_off2_.p,
                                            reinterpret_cast<Strm*>(d_accum_.p), 0);
-    k_post_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(d_accum_.p), d_mval_.p,
-                                       d_mstart_.p, d_nstep2_.p, d_off2_.p, d_sig2_.p, lmax_,
-                                       reinterpret_cast<double2*>(d_alm),
-                                       reinterpret_cast<double2*>(d_alm) + alm_cstride, 0);
-    launches_ += 2;
+    ++launches_;
+    sums = d_accum_.p;
   }
+  if (spin == 0)
+    k_post_s0<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(sums), d_mval_.p, d_mstart_.p, d_nstep0_.p,
+                                       d_off0_.p, d_invs0_.p, lmax_, reinterpret_cast<double2*>(d_alm), 0);
+  else
+    k_post_s2<<<grid, TB, 0, stream>>>(reinterpret_cast<const Strm*>(sums), d_mval_.p, d_mstart_.p, d_nstep2_.p,
+                                       d_off2_.p, d_sig2_.p, lmax_, reinterpret_cast<double2*>(d_alm),
+                                       reinterpret_cast<double2*>(d_alm) + alm_cstride, 0);
+  ++launches_;
   HP_CUDA(cudaGetLastError());
 }
 

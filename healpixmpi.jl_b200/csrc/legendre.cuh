@@ -118,6 +118,7 @@ class LegendreStage {
   LegLayout layout_;
   LegendreTables tab_;
   bool have0_ = false, have2_ = false;
+  bool direct0_ = false, direct2_ = false;   // adjoint partial rows already are the per-m sums
   double culled0_ = 0, culled2_ = 0, dense_ = 0;
   int64_t launches_ = 0;
   size_t dev_bytes_ = 0;

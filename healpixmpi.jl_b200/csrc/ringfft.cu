@@ -115,18 +115,21 @@ struct Phase {
 //   INV = false: exp(-2 pi i jk/M);  INV = true: exp(+2 pi i jk/M).  Unnormalised.
 //   tw: two-level shared-memory table of the T-th roots exp(-2 pi i k / T), T >= M.
 // ------------------------------------------------------------------------------------------------
+// `nb` transforms of length M stored back to back (buf + b * M) advance through the passes together
 template <bool INV>
-__device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt) {
+__device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt, int nb = 1) {
   if (M < 2) return;
   const int lg = 31 - __clz(M);
   int L = M;
   if (lg & 1) {
     const int h = L >> 1;
     const int ts = tw.T / L;
-    for (int i = tid; i < h; i += nt) {
-      const double2 a = buf[i], b = buf[i + h];
-      buf[i] = cadd(a, b);
-      buf[i + h] = cmul(csub(a, b), tw.get<INV>(i * ts));
+    for (int t = tid; t < h * nb; t += nt) {
+      const int i = t & (h - 1);
+      double2* p = buf + (t >> (lg - 1)) * M;
+      const double2 a = p[i], b = p[i + h];
+      p[i] = cadd(a, b);
+      p[i + h] = cmul(csub(a, b), tw.get<INV>(i * ts));
     }
     L >>= 1;
     __syncthreads();
@@ -135,18 +138,20 @@ __device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt) {
     const int q = L >> 2;
     const int lq = 31 - __clz(q);
     const int ts = tw.T / L;
-    for (int i = tid; i < (M >> 2); i += nt) {
+    for (int t = tid; t < (M >> 2) * nb; t += nt) {
+      const int i = t & ((M >> 2) - 1);
+      double2* p = buf + (t >> (lg - 2)) * M;
       const int j = i & (q - 1);
       const int b = ((i >> lq) * L) + j;
-      const double2 x0 = buf[b], x1 = buf[b + q], x2 = buf[b + 2 * q], x3 = buf[b + 3 * q];
+      const double2 x0 = p[b], x1 = p[b + q], x2 = p[b + 2 * q], x3 = p[b + 3 * q];
       const double2 w1 = tw.get<INV>(j * ts);
       const double2 w2 = make_double2(fma(w1.x, w1.x, -w1.y * w1.y), 2.0 * w1.x * w1.y);  // w1^2
       const double2 a0 = cadd(x0, x2), a2 = cmul(csub(x0, x2), w1);
       const double2 a1 = cadd(x1, x3), a3 = mul_pm_i<INV>(cmul(csub(x1, x3), w1));
-      buf[b] = cadd(a0, a1);
-      buf[b + q] = cmul(csub(a0, a1), w2);
-      buf[b + 2 * q] = cadd(a2, a3);
-      buf[b + 3 * q] = cmul(csub(a2, a3), w2);
+      p[b] = cadd(a0, a1);
+      p[b + q] = cmul(csub(a0, a1), w2);
+      p[b + 2 * q] = cadd(a2, a3);
+      p[b + 3 * q] = cmul(csub(a2, a3), w2);
     }
     L >>= 2;
     __syncthreads();
@@ -154,15 +159,17 @@ __device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt) {
 }
 
 template <bool INV>
-__device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt) {
+__device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt, int nb = 1) {
   if (M < 2) return;
   const int lg = 31 - __clz(M);
   int L = 1;
   if (lg & 1) {
-    for (int i = tid; i < (M >> 1); i += nt) {
-      const double2 a = buf[2 * i], b = buf[2 * i + 1];
-      buf[2 * i] = cadd(a, b);
-      buf[2 * i + 1] = csub(a, b);
+    for (int t = tid; t < (M >> 1) * nb; t += nt) {
+      const int i = t & ((M >> 1) - 1);
+      double2* p = buf + (t >> (lg - 1)) * M;
+      const double2 a = p[2 * i], b = p[2 * i + 1];
+      p[2 * i] = cadd(a, b);
+      p[2 * i + 1] = csub(a, b);
     }
     L = 2;
     __syncthreads();
@@ -172,24 +179,28 @@ __device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt) {
     const int q = L >> 2;
     const int lq = 31 - __clz(q);
     const int ts = tw.T / L;
-    for (int i = tid; i < (M >> 2); i += nt) {
+    for (int t = tid; t < (M >> 2) * nb; t += nt) {
+      const int i = t & ((M >> 2) - 1);
+      double2* p = buf + (t >> (lg - 2)) * M;
       const int j = i & (q - 1);
       const int b = ((i >> lq) * L) + j;
-      const double2 x0 = buf[b], x1 = buf[b + q], x2 = buf[b + 2 * q], x3 = buf[b + 3 * q];
+      const double2 x0 = p[b], x1 = p[b + q], x2 = p[b + 2 * q], x3 = p[b + 3 * q];
       const double2 w1 = tw.get<INV>(j * ts);
       const double2 w2 = make_double2(fma(w1.x, w1.x, -w1.y * w1.y), 2.0 * w1.x * w1.y);  // w1^2
       const double2 t1 = cmul(x1, w2), t3 = cmul(x3, w2);
       const double2 a0 = cadd(x0, t1), a1 = csub(x0, t1);
       const double2 a2 = cadd(x2, t3), a3 = csub(x2, t3);
       const double2 s2 = cmul(a2, w1), s3 = mul_pm_i<INV>(cmul(a3, w1));
-      buf[b] = cadd(a0, s2);
-      buf[b + 2 * q] = csub(a0, s2);
-      buf[b + q] = cadd(a1, s3);
-      buf[b + 3 * q] = csub(a1, s3);
+      p[b] = cadd(a0, s2);
+      p[b + 2 * q] = csub(a0, s2);
+      p[b + q] = cadd(a1, s3);
+      p[b + 3 * q] = csub(a1, s3);
     }
     __syncthreads();
   }
 }
+
+__device__ __forceinline__ int brev_idx(int i, int lg) { return lg ? (int)(__brev((unsigned)i) >> (32 - lg)) : 0; }
 
 __device__ void bitrev_permute(double2* buf, int M, int tid, int nt) {
   if (M < 4) return;  // M = 1, 2: identity
@@ -374,16 +385,17 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
   double* out = map + (int64_t)comp * map_cstride + d.pixoff;
   const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (d.M == 0) {
-    // power-of-two r: both halves transformed in place, one fully coalesced store
-    idft_r(S.A, S.A, r, 0, nullptr, W, TW, tid, nt);
-    idft_r(S.A + r, S.A + r, r, 0, nullptr, W, TW, tid, nt);
+    // power-of-two r: both halves transformed in place (DIF: results in bit-reversed order, read back
+    // through the reversed index instead of a separate permutation pass), one fully coalesced store
+    fft_dif<true>(S.A, r, TW, tid, nt, 2);
+    const int lgr = 31 - __clz(r);
     // ---- pixels: x[4j..4j+3] = Re U[j], Im U[j], Re V[j], Im V[j] ----
     if (al16) {
       double2* out2 = reinterpret_cast<double2*>(out);
-      for (int t = tid; t < N; t += nt) out2[t] = (t & 1) ? S.A[r + (t >> 1)] : S.A[t >> 1];
+      for (int t = tid; t < N; t += nt) out2[t] = S.A[((t & 1) ? r : 0) + brev_idx(t >> 1, lgr)];
     } else {
       for (int t = tid; t < N; t += nt) {
-        const double2 v = (t & 1) ? S.A[r + (t >> 1)] : S.A[t >> 1];
+        const double2 v = S.A[((t & 1) ? r : 0) + brev_idx(t >> 1, lgr)];
         out[2 * t] = v.x;
         out[2 * t + 1] = v.y;
       }
@@ -434,22 +446,26 @@ __global__ void __launch_bounds__(1024) k_map2leg(const RingDesc* __restrict__ d
   const double* in = map + (int64_t)comp * map_cstride + d.pixoff;
   const bool al16 = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   double2* vdst = d.M == 0 ? S.A + r : S.B;  // Bluestein: v parks in B while A is the work array
+  // power-of-two r: stored in bit-reversed order so that the DIT passes below deliver natural order
+  const int lgr = d.M == 0 ? 31 - __clz(r) : -1;
   if (al16) {
     const double2* in2 = reinterpret_cast<const double2*>(in);
     for (int t = tid; t < N; t += nt) {
       const double2 v = in2[t];
-      ((t & 1) ? vdst : S.A)[t >> 1] = make_double2(v.x, -v.y);
+      const int j = lgr >= 0 ? brev_idx(t >> 1, lgr) : (t >> 1);
+      ((t & 1) ? vdst : S.A)[j] = make_double2(v.x, -v.y);
     }
   } else {
-    for (int t = tid; t < N; t += nt)
-      ((t & 1) ? vdst : S.A)[t >> 1] = make_double2(in[2 * t], -in[2 * t + 1]);
+    for (int t = tid; t < N; t += nt) {
+      const int j = lgr >= 0 ? brev_idx(t >> 1, lgr) : (t >> 1);
+      ((t & 1) ? vdst : S.A)[j] = make_double2(in[2 * t], -in[2 * t + 1]);
+    }
   }
   __syncthreads();
 
   const double2* hhat = d.hoff >= 0 ? hhat_all + d.hoff : nullptr;
   if (d.M == 0) {
-    idft_r(S.A, S.A, r, 0, nullptr, W, TW, tid, nt);          // = conj(Uhat)
-    idft_r(S.A + r, S.A + r, r, 0, nullptr, W, TW, tid, nt);  // = conj(Vhat)
+    fft_dit<true>(S.A, r, TW, tid, nt, 2);  // = conj(Uhat) | conj(Vhat)
   } else {
     idft_r(S.A, S.A, r, d.M, hhat, W, TW, tid, nt);  // conj(Uhat) in A[0..r)
     for (int k = tid; k < r; k += nt) {                   // swap: conj(Uhat) -> B, conj(v) -> A
