@@ -242,6 +242,33 @@ def test_fused_alm2map_and_adjoint(H, O, nside, lmax, spin):
     plan.destroy()
 
 
+@pytest.mark.parametrize("nside,lmax", [(1, 2), (1, 0), (2, 1), (2, 9), (4, 30), (8, 3)])
+@pytest.mark.parametrize("spin", [0, 2])
+def test_edge_sizes(H, O, nside, lmax, spin):
+    """Degenerate and heavily aliased sizes: nside 1 (rings of 4 pixels), lmax 0 / 1 (spin 2 has no l >= 2: all
+    zero), lmax well above 2 nside (every ring folds many m onto itself), lmax far below nside."""
+    plan, alm, alm_loc, idx, full, pix = _fused(H, O, nside, lmax, spin, 7 * nside + lmax + spin)
+    ncomp = alm.shape[0]
+    ref, _ = O.full_alm2map(alm, spin, nside, lmax)
+    ref = ref.astype(np.float64)
+    scale = max(np.linalg.norm(ref), 1e-300)
+    assert np.linalg.norm(full - ref) <= TOL * scale + (0 if np.any(ref) else 0), (full, ref)
+    if spin == 2 and lmax < 2:
+        assert not np.any(full)
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal((ncomp, 12 * nside * nside))
+    out = np.full((ncomp, plan.nalm_loc), np.nan + 0j)
+    plan.adjoint_alm2map(np.ascontiguousarray(f[:, pix]), out, ncomp)
+    refa = O.full_adjoint(f, spin, nside, lmax).astype(np.complex128)[:, idx]
+    if spin == 2:
+        mval, mstart0 = plan.alm_info()
+        for mi, m in enumerate(mval):
+            for l in range(m, min(2, lmax + 1)):
+                refa[:, mstart0[mi] + l] = 0
+    assert np.linalg.norm(out - refa) <= TOL * max(np.linalg.norm(refa), 1e-300), (out, refa)
+    plan.destroy()
+
+
 def test_golden_fixtures(H, O):
     """Committed golden vectors (tests/golden, produced by tests/golden/make_golden.py from the
     oracle): seeded alm2map at nside 16 and the reference's own deterministic adjoint case
