@@ -942,10 +942,12 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     if ((a.M != 0) != (b.M != 0)) return (a.M != 0) > (b.M != 0);
     return ca > cb;
   });
+  // shared memory per CTA follows the largest ring of a class: keep the M = 8192 Bluestein rings (221 KB, one
+  // CTA per SM) apart from the M = 4096 ones (two CTAs per SM)
   auto bucket = [](const RingDesc& d) {
     const int work = d.M ? d.M : d.r;
-    const int b = work > 2048 ? 3 : (work > 512 ? 2 : (work > 64 ? 1 : 0));
-    return (d.M ? 4 : 0) + b;
+    const int b = work > 4096 ? 4 : (work > 2048 ? 3 : (work > 512 ? 2 : (work > 64 ? 1 : 0)));
+    return (d.M ? 8 : 0) + b;
   };
   for (size_t i = 0; i < desc_.size();) {
     size_t j = i;
@@ -962,6 +964,9 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     const char* ev = getenv("HPSHT_FFT_THREADS_BIG");
     const int big = ev ? atoi(ev) : 1024;
     c.threads = work > 2048 ? big : (work > 512 ? 256 : (work > 64 ? 128 : 64));
+    // 64 registers x 1024 threads fill an SM's register file: a class whose shared memory would let two CTAs
+    // share an SM gets 512 threads so that they actually can (one loads while the other transforms)
+    if (c.threads == 1024 && smem_bytes(c.rmax, c.Mmax, 512) <= 113 * 1024) c.threads = 512;
     c.smem = smem_bytes(c.rmax, c.Mmax, c.threads);
     classes_.push_back(c);
     i = j;
