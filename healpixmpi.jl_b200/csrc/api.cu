@@ -447,6 +447,10 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
   int64_t extra = 0;
   const size_t alm_d = (size_t)nalm_loc * ncomp * 2, map_d = (size_t)npix_loc * ncomp;
   const bool in_dev = is_device_pointer(in), out_dev = is_device_pointer(out);
+  // Device pointers: whoever produced `in` (or last touched `out`) did so on a stream this library does
+  // not know -- e.g. the caller's framework filling the buffer a moment ago -- while the plan works on its
+  // own non-blocking streams.  Wait for the device once on entry; on return the call is complete.
+  if (in_dev || out_dev) HP_CUDA(cudaDeviceSynchronize());
   if (!tm) tm.reset(new Timer());
   cudaEvent_t* e = tm->ev;
   HP_CUDA(cudaEventRecord(e[0], stream));
@@ -461,7 +465,7 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
   // [0, mi_split): the rest of the alm copy overlaps that block's Legendre work
   const int spin = ncomp == 1 ? 0 : 2;
   const int mi_split = HB > 1 ? leg.block_mi_end(0, spin) : (int)nm_loc;
-  const bool split_alm = mi_split > 0 && mi_split < (int)nm_loc;
+  const bool split_alm = mi_split > 0 && mi_split < (int)nm_loc && !getenv("HPSHT_NO_ALM_STREAM");
   // alm elements of the local m's [0, mi_split) form a prefix of every component
   const size_t a_split = split_alm ? (size_t)(mstart[(size_t)mi_split] + mval[(size_t)mi_split]) : 0;
   const bool stream_alm_in = pipe_out && !in_dev && split_alm;
@@ -599,13 +603,12 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
       HP_CUDA(cudaEventRecord(ev_ready, stream));
       HP_CUDA(cudaStreamWaitEvent(fstream, ev_ready, 0));
     }
-    // the local m's >= mi_split are complete before the last (polar) block starts: post-process and
-    // copy them out on the side streams while that block computes
+    // the local m's >= mi_split are complete before the last (polar) block starts: post-process them on
+    // the compute stream right there (a ~1 ms kernel) and copy them out on the copy stream while that block
+    // computes
     auto early_alm_out = [&]() {
-      HP_CUDA(cudaEventRecord(ev_a0, stream));  // every earlier block has been accumulated
-      HP_CUDA(cudaStreamWaitEvent(pstream, ev_a0, 0));
-      leg.leg2alm_blocks_end(d_out, nalm_loc, ncomp, pstream, mi_split, (int)nm_loc);
-      HP_CUDA(cudaEventRecord(ev_a1, pstream));
+      leg.leg2alm_blocks_end(d_out, nalm_loc, ncomp, stream, mi_split, (int)nm_loc);
+      HP_CUDA(cudaEventRecord(ev_a1, stream));
       HP_CUDA(cudaStreamWaitEvent(hstream, ev_a1, 0));
       for (int c = 0; c < ncomp; ++c) {
         const size_t o = ((size_t)c * nalm_loc + a_split) * 2;
@@ -823,13 +826,20 @@ int64_t alm_extent(int64_t lmax, int64_t nm, const int64_t* mval, const int64_t*
 
 // stage a (possibly host) input on the device; returns the device pointer to use
 const double* stage_in(const double* p, size_t n, DevBuf<double>& buf) {
-  if (is_device_pointer(p)) return p;
+  if (is_device_pointer(p)) {
+    // produced on a stream this library does not know (see hpsht_plan::run): wait for the device
+    HP_CUDA(cudaDeviceSynchronize());
+    return p;
+  }
   buf.ensure(n);
   HP_CUDA(cudaMemcpy(buf.p, p, n * sizeof(double), cudaMemcpyHostToDevice));
   return buf.p;
 }
 double* stage_out(double* p, size_t n, DevBuf<double>& buf) {
-  if (is_device_pointer(p)) return p;
+  if (is_device_pointer(p)) {
+    HP_CUDA(cudaDeviceSynchronize());  // earlier work of the caller on this buffer must not land after ours
+    return p;
+  }
   buf.ensure(n);
   return buf.p;
 }
