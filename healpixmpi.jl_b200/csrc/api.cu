@@ -155,7 +155,6 @@ struct hpsht_plan {
   cudaStream_t hstream = nullptr;       // host <-> device copies
   cudaStream_t fstream = nullptr;       // P>1: ring FFT + pack/unpack of a block (next to the Legendre stream)
   cudaEvent_t ev_hdone = nullptr, ev_a0 = nullptr, ev_a1 = nullptr;
-  cudaStream_t pstream = nullptr;       // early post-processing of finished m's (adjoint)
   int64_t blo(int b, int t) const { return bj_lo[(size_t)b * P + t]; }
   int64_t bhi(int b, int t) const { return bj_hi[(size_t)b * P + t]; }
   int64_t pix_lo(int b) const { return blo(b, rank) < nr_loc ? rstart[(size_t)blo(b, rank)] : npix_loc; }
@@ -364,7 +363,6 @@ void hpsht_plan::setup_blocks() {
   HP_CUDA(cudaEventCreateWithFlags(&ev_hdone, cudaEventDisableTiming));
   HP_CUDA(cudaEventCreateWithFlags(&ev_a0, cudaEventDisableTiming));
   HP_CUDA(cudaEventCreateWithFlags(&ev_a1, cudaEventDisableTiming));
-  HP_CUDA(cudaStreamCreateWithPriority(&pstream, cudaStreamNonBlocking, prio_hi));
 }
 
 // the leg pieces of ring block b: per peer and component one contiguous run of rows on both sides
@@ -714,7 +712,6 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
   if (cstream) HP_CUDA(cudaStreamSynchronize(cstream));
   if (fstream) HP_CUDA(cudaStreamSynchronize(fstream));
   if (hstream) HP_CUDA(cudaStreamSynchronize(hstream));
-  if (pstream) HP_CUDA(cudaStreamSynchronize(pstream));
   auto el = [&](int a, int b) {
     float f = 0;
     cudaEventElapsedTime(&f, e[a], e[b]);
@@ -1126,7 +1123,6 @@ int hpsht_plan_destroy(hpsht_plan* plan) {
     for (auto& e : plan->ev_x) cudaEventDestroy(e);
     for (auto& e : plan->ev_f) cudaEventDestroy(e);
     if (plan->fstream) cudaStreamDestroy(plan->fstream);
-    if (plan->pstream) cudaStreamDestroy(plan->pstream);
     if (plan->ev_a0) cudaEventDestroy(plan->ev_a0);
     if (plan->ev_a1) cudaEventDestroy(plan->ev_a1);
     if (plan->ev_hdone) cudaEventDestroy(plan->ev_hdone);
