@@ -177,7 +177,11 @@ int hpsht_plan_alm2cl(hpsht_plan* plan, const double* alm1, const double* alm2, 
 
 /* Per-stage device times (ms, CUDA events) of the most recent fused call on this plan:
    [0] total, [1] the Legendre recurrence kernel alone, [2] whole Legendre stage (with the O(nalm)
-   prep / reduce / post kernels), [3] all-to-all (+pack/unpack), [4] ring FFT, [5] H2D, [6] D2H.                                                       */
+   prep / reduce / post kernels), [3] all-to-all (+pack/unpack), [4] ring FFT, [5] H2D, [6] D2H.
+   Host-pointer calls run ring block by ring block with the copies on their own stream, so there the
+   stages overlap: [0] stays the whole call, [1]/[2] span first to last Legendre block (the ring FFTs of
+   the blocks in between included), [4] is the last block's FFT, [5]/[6] only the copies that were not
+   hidden.  The per-stage figures `bench.py` reports come from device-pointer calls.       */
 #define HPSHT_NTIMES 8
 int hpsht_plan_timings(const hpsht_plan* plan, double ms[HPSHT_NTIMES]);
 /* Number of kernel launches issued by the most recent fused call.                       */
