@@ -115,8 +115,16 @@ struct Phase {
 //   INV = false: exp(-2 pi i jk/M);  INV = true: exp(+2 pi i jk/M).  Unnormalised.
 //   tw: two-level shared-memory table of the T-th roots exp(-2 pi i k / T), T >= M.
 // ------------------------------------------------------------------------------------------------
+// Physical position of logical element i in a swizzled work array: the low three index bits are XORed with
+// bits 2..4, a permutation inside every aligned group of 8 elements.  With 16-byte elements a quarter-warp
+// then hits eight distinct 4-bank groups in EVERY radix-4 pass (quarter lengths 1, 4, 16, ...), where the plain
+// layout is 4-way (q = 1) and 2-way (q = 4) conflicted -- tools/proto/fft_bank_model.py reproduces the 36 %
+// replay excess ncu reports for M = 8192 and shows 0 % with this map.
+template <bool SWZ>
+__device__ __forceinline__ int swz(int i) { return SWZ ? (i ^ ((i >> 2) & 7)) : i; }
+
 // `nb` transforms of length M stored back to back (buf + b * M) advance through the passes together
-template <bool INV>
+template <bool INV, bool SWZ = false>
 __device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt, int nb = 1) {
   if (M < 2) return;
   const int lg = 31 - __clz(M);
@@ -127,9 +135,9 @@ __device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt, int 
     for (int t = tid; t < h * nb; t += nt) {
       const int i = t & (h - 1);
       double2* p = buf + (t >> (lg - 1)) * M;
-      const double2 a = p[i], b = p[i + h];
-      p[i] = cadd(a, b);
-      p[i + h] = cmul(csub(a, b), tw.get<INV>(i * ts));
+      const double2 a = p[swz<SWZ>(i)], b = p[swz<SWZ>(i + h)];
+      p[swz<SWZ>(i)] = cadd(a, b);
+      p[swz<SWZ>(i + h)] = cmul(csub(a, b), tw.get<INV>(i * ts));
     }
     L >>= 1;
     __syncthreads();
@@ -143,22 +151,23 @@ __device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt, int 
       double2* p = buf + (t >> (lg - 2)) * M;
       const int j = i & (q - 1);
       const int b = ((i >> lq) * L) + j;
-      const double2 x0 = p[b], x1 = p[b + q], x2 = p[b + 2 * q], x3 = p[b + 3 * q];
+      const int i0 = swz<SWZ>(b), i1 = swz<SWZ>(b + q), i2 = swz<SWZ>(b + 2 * q), i3 = swz<SWZ>(b + 3 * q);
+      const double2 x0 = p[i0], x1 = p[i1], x2 = p[i2], x3 = p[i3];
       const double2 w1 = tw.get<INV>(j * ts);
       const double2 w2 = make_double2(fma(w1.x, w1.x, -w1.y * w1.y), 2.0 * w1.x * w1.y);  // w1^2
       const double2 a0 = cadd(x0, x2), a2 = cmul(csub(x0, x2), w1);
       const double2 a1 = cadd(x1, x3), a3 = mul_pm_i<INV>(cmul(csub(x1, x3), w1));
-      p[b] = cadd(a0, a1);
-      p[b + q] = cmul(csub(a0, a1), w2);
-      p[b + 2 * q] = cadd(a2, a3);
-      p[b + 3 * q] = cmul(csub(a2, a3), w2);
+      p[i0] = cadd(a0, a1);
+      p[i1] = cmul(csub(a0, a1), w2);
+      p[i2] = cadd(a2, a3);
+      p[i3] = cmul(csub(a2, a3), w2);
     }
     L >>= 2;
     __syncthreads();
   }
 }
 
-template <bool INV>
+template <bool INV, bool SWZ = false>
 __device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt, int nb = 1) {
   if (M < 2) return;
   const int lg = 31 - __clz(M);
@@ -167,9 +176,10 @@ __device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt, int 
     for (int t = tid; t < (M >> 1) * nb; t += nt) {
       const int i = t & ((M >> 1) - 1);
       double2* p = buf + (t >> (lg - 1)) * M;
-      const double2 a = p[2 * i], b = p[2 * i + 1];
-      p[2 * i] = cadd(a, b);
-      p[2 * i + 1] = csub(a, b);
+      const int ia = swz<SWZ>(2 * i), ib = swz<SWZ>(2 * i + 1);
+      const double2 a = p[ia], b = p[ib];
+      p[ia] = cadd(a, b);
+      p[ib] = csub(a, b);
     }
     L = 2;
     __syncthreads();
@@ -184,17 +194,18 @@ __device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt, int 
       double2* p = buf + (t >> (lg - 2)) * M;
       const int j = i & (q - 1);
       const int b = ((i >> lq) * L) + j;
-      const double2 x0 = p[b], x1 = p[b + q], x2 = p[b + 2 * q], x3 = p[b + 3 * q];
+      const int i0 = swz<SWZ>(b), i1 = swz<SWZ>(b + q), i2 = swz<SWZ>(b + 2 * q), i3 = swz<SWZ>(b + 3 * q);
+      const double2 x0 = p[i0], x1 = p[i1], x2 = p[i2], x3 = p[i3];
       const double2 w1 = tw.get<INV>(j * ts);
       const double2 w2 = make_double2(fma(w1.x, w1.x, -w1.y * w1.y), 2.0 * w1.x * w1.y);  // w1^2
       const double2 t1 = cmul(x1, w2), t3 = cmul(x3, w2);
       const double2 a0 = cadd(x0, t1), a1 = csub(x0, t1);
       const double2 a2 = cadd(x2, t3), a3 = csub(x2, t3);
       const double2 s2 = cmul(a2, w1), s3 = mul_pm_i<INV>(cmul(a3, w1));
-      p[b] = cadd(a0, s2);
-      p[b + 2 * q] = csub(a0, s2);
-      p[b + q] = cadd(a1, s3);
-      p[b + 3 * q] = csub(a1, s3);
+      p[i0] = cadd(a0, s2);
+      p[i2] = csub(a0, s2);
+      p[i1] = cadd(a1, s3);
+      p[i3] = csub(a1, s3);
     }
     __syncthreads();
   }
@@ -228,23 +239,38 @@ __device__ void idft_r(double2* A, const double2* src, int r, int M, const doubl
     return;
   }
   const int two_r = 2 * r;
+  // The work array is kept in the swizzled layout (swz<true>) between the chirp multiply and the final
+  // one.  Both boundary loops may run in place (src == A, result in A[0..r)): the swizzle permutes inside
+  // aligned groups of 8 elements, which one warp handles in one iteration, so "all lanes read, __syncwarp,
+  // all lanes write" is enough; the loops are uniform (every thread runs every iteration).
   // chirp c[k] = exp(i pi k^2 / r) = W(2 (k^2 mod 2r))
-  for (int k = tid; k < M; k += nt) {
+  for (int kb = 0; kb < M; kb += nt) {
+    const int k = kb + tid;
     double2 v = make_double2(0.0, 0.0);
     if (k < r) {
       const int q = (int)(((unsigned)k * (unsigned)k) % (unsigned)two_r);
       v = cmul(src[k], W(2 * q));
     }
-    A[k] = v;
+    __syncwarp();
+    if (k < M) A[swz<true>(k)] = v;
   }
   __syncthreads();
-  fft_dif<false>(A, M, tw, tid, nt);
-  for (int k = tid; k < M; k += nt) A[k] = cmul(A[k], __ldg(&hhat[k]));
+  fft_dif<false, true>(A, M, tw, tid, nt);
+  for (int k = tid; k < M; k += nt) {
+    const int p = swz<true>(k);
+    A[p] = cmul(A[p], __ldg(&hhat[k]));
+  }
   __syncthreads();
-  fft_dit<true>(A, M, tw, tid, nt);
-  for (int k = tid; k < r; k += nt) {
-    const int q = (int)(((unsigned)k * (unsigned)k) % (unsigned)two_r);
-    A[k] = cmul(A[k], W(2 * q));
+  fft_dit<true, true>(A, M, tw, tid, nt);
+  for (int kb = 0; kb < r; kb += nt) {
+    const int k = kb + tid;
+    double2 v = make_double2(0.0, 0.0);
+    if (k < r) {
+      const int q = (int)(((unsigned)k * (unsigned)k) % (unsigned)two_r);
+      v = cmul(A[swz<true>(k)], W(2 * q));
+    }
+    __syncwarp();
+    if (k < r) A[k] = v;
   }
   __syncthreads();
 }
