@@ -55,6 +55,9 @@ SIGNATURES = {
     "hpsht_plan_map_info": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "hpsht_alm2map": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
     "hpsht_adjoint_alm2map": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
+    "hpsht_alm2map_async": (C.c_int, [vp, vp, vp, C.c_int, vp]),
+    "hpsht_adjoint_alm2map_async": (C.c_int, [vp, vp, vp, C.c_int, vp]),
+    "hpsht_plan_synchronize": (C.c_int, [vp]),
     "hpsht_plan_scatter_alm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
     "hpsht_plan_gather_alm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
     "hpsht_plan_scatter_map": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),

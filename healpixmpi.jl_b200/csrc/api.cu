@@ -34,21 +34,17 @@ void require_device() {
 }
 
 // ---- exchange pack / unpack (map-side leg <-> per-peer blocks) ----
-// legF[(comp*nr_loc + j)*nm_tot + m]  <->  block of source s = m % P, laid out [m-slab][comp][ring][m in slab]:
-//   boff[s] + nr_loc*(ncs*sstart + comp*nms) + j*nms + (i - sstart),   i = m / P (local m index on s),
-//   slabs of K-th parts of s's nm_s local m's (ms = ceil(nm_s / K)).
+// legF[(comp*nr_loc + j)*nm_tot + m]  <->  block of source s = m % P, laid out like the reference's receive
+// buffer (src/sht.jl:35-42): boff[s] + (comp*nr_loc + j)*nm_s + i,  i = m / P (local m index on s).
 struct ExchGeom {
   int64_t nm_tot, nr_loc, mmax;
-  int P, K, ncs;
+  int P;
 };
 __device__ __forceinline__ int64_t mapside_off(const ExchGeom& g, const int64_t* boff, int64_t m, int64_t j, int comp) {
   const int s = (int)(m % g.P);
   const int64_t i = m / g.P;
   const int64_t nm_s = (g.mmax + g.P - s) / g.P;
-  const int64_t ms = (nm_s + g.K - 1) / g.K;
-  const int64_t ss = (i / ms) * ms;
-  const int64_t ns = min(ms, nm_s - ss);
-  return boff[s] + g.nr_loc * ((int64_t)g.ncs * ss + (int64_t)comp * ns) + j * ns + (i - ss);
+  return boff[s] + ((int64_t)comp * g.nr_loc + j) * nm_s + i;
 }
 // rows j0 .. j0+nj-1 of every component (the whole array: j0 = 0, nj = nr_loc)
 __global__ void k_unpack(const double2* __restrict__ mapside, const int64_t* __restrict__ boff,
@@ -130,12 +126,11 @@ struct hpsht_plan {
   int64_t nm_loc = 0, nalm_loc = 0, nr_loc = 0, npix_loc = 0, nr_tot = 0, nm_tot = 0;
   bool stages_ready = false;
 
-  cudaStream_t stream = nullptr;   // compute
-  cudaStream_t cstream = nullptr;  // NCCL exchange (overlaps the Legendre work of the next m-slab)
-  int K = 1;                       // m-slabs per rank
-  std::vector<cudaEvent_t> ev_slab, ev_done;
-  std::vector<cudaStream_t> sstream;  // one per m-slab: adjoint slab kernels run concurrently (no wave tails)
-  cudaEvent_t ev_ready = nullptr;
+  cudaStream_t stream = nullptr;   // Legendre stage
+  cudaStream_t cstream = nullptr;  // NCCL exchange of a ring block (overlaps the Legendre work of the next block)
+  cudaStream_t fstream = nullptr;  // P>1: ring FFT + pack/unpack of a block
+  cudaStream_t hstream = nullptr;  // host -> device copies (and all copies of single-direction calls)
+  cudaStream_t ostream = nullptr;  // device -> host copies
   LegendreStage leg;
   RingFFT fft;
   DevBuf<double> legF;      // map-side leg [ncomp][nr_loc][nm_tot] (complex)
@@ -147,31 +142,32 @@ struct hpsht_plan {
   RankAlmDesc own_alm;                  // shard ops (shards.cuh): this rank's descriptors, built lazily
   RankMapDesc own_map;
   DevBuf<double> shard_scratch;
-  // single-rank host-pointer calls: ring blocks pipelined against the PCIe copies of the map
+  // Ring blocks (block set 1 of the Legendre stage): HB ranges of the global pole -> equator pair list.  Used
+  // to pipeline Legendre(b) / exchange(b) / ring FFT(b) / PCIe copy(b); HB is derived from quantities that
+  // are identical on every rank.
   int HB = 1;
+  bool dev_blocks = true;               // P>1: device-pointer calls run block by block too (exchange overlap)
   std::vector<std::unique_ptr<RingFFT>> fftb;
   std::vector<int64_t> bj_lo, bj_hi;    // [block][rank]: local ring range of the block on that rank
   std::vector<cudaEvent_t> ev_blk, ev_x, ev_f;
-  cudaStream_t hstream = nullptr;       // host <-> device copies
-  cudaStream_t fstream = nullptr;       // P>1: ring FFT + pack/unpack of a block (next to the Legendre stream)
-  cudaEvent_t ev_hdone = nullptr, ev_a0 = nullptr, ev_a1 = nullptr;
-  int64_t blo(int b, int t) const { return bj_lo[(size_t)b * P + t]; }
-  int64_t bhi(int b, int t) const { return bj_hi[(size_t)b * P + t]; }
-  int64_t pix_lo(int b) const { return blo(b, rank) < nr_loc ? rstart[(size_t)blo(b, rank)] : npix_loc; }
-  int64_t pix_hi(int b) const { return bhi(b, rank) < nr_loc ? rstart[(size_t)bhi(b, rank)] : npix_loc; }
+  cudaEvent_t ev_hdone = nullptr, ev_a0 = nullptr, ev_a1 = nullptr, ev_entry = nullptr, ev_user = nullptr,
+              ev_done = nullptr;
+  int64_t blo(int set, int b, int t) const { return set ? bj_lo[(size_t)b * P + t] : 0; }
+  int64_t bhi(int set, int b, int t) const { return set ? bj_hi[(size_t)b * P + t] : nr_of[(size_t)t]; }
+  int64_t pix_at(int64_t j) const { return j < nr_loc ? rstart[(size_t)j] : npix_loc; }
   void setup_blocks();
-  void exchange_block(bool synthesis, int ncomp, int b, cudaStream_t st);
+  void exchange_block(bool synthesis, int ncomp, int set, int b, cudaStream_t st);
   ncclComm_t comm = nullptr;
   std::unique_ptr<Timer> tm;
   double ms[HPSHT_NTIMES] = {0};
+  bool times_pending = false, last_synthesis = true;
   int64_t n_launch = 0;
 
   void build_shard();
   void ensure_stages();
-  void exchange_slab(bool synthesis, int ncomp, int slab, cudaStream_t st);
-  int64_t slab_start(int q, int slab) const;
-  int64_t slab_size(int q, int slab) const;
-  void run(bool synthesis, const double* in, double* out, int ncomp);
+  void run(bool synthesis, const double* in, double* out, int ncomp, bool async, cudaStream_t user);
+  void synchronize();
+  void finish_times();
 };
 
 void hpsht_plan::build_shard() {
@@ -215,17 +211,6 @@ void hpsht_plan::build_shard() {
   }
 }
 
-// m-slab `slab` of rank q: local m indices [slab_start, slab_start + slab_size)
-int64_t hpsht_plan::slab_start(int q, int slab) const {
-  const int64_t ms = (nm_of[(size_t)q] + K - 1) / K;
-  return std::min<int64_t>((int64_t)slab * ms, nm_of[(size_t)q]);
-}
-int64_t hpsht_plan::slab_size(int q, int slab) const {
-  const int64_t ms = (nm_of[(size_t)q] + K - 1) / K;
-  const int64_t ss = slab_start(q, slab);
-  return std::max<int64_t>(0, std::min<int64_t>(ms, nm_of[(size_t)q] - ss));
-}
-
 void hpsht_plan::ensure_stages() {
   if (stages_ready) return;
   // ---- leg layout seen by the Legendre kernels: ring slots in thetatot order ----
@@ -233,9 +218,10 @@ void hpsht_plan::ensure_stages() {
   lay.a0.resize((size_t)nr_tot);
   lay.nr.resize((size_t)nr_tot);
   lay.j.resize((size_t)nr_tot);
+  int prio_lo = 0, prio_hi = 0;
+  HP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   if (P == 1) {
     // single rank: the Legendre stage reads/writes the map-side array directly (src/sht.jl:87-88)
-    K = 1;
     for (int64_t s = 0; s < nr_tot; ++s) {
       lay.a0[(size_t)s] = 0;
       lay.nr[(size_t)s] = nr_loc;
@@ -243,12 +229,7 @@ void hpsht_plan::ensure_stages() {
     }
     legF.alloc((size_t)max_ncomp * nr_loc * nm_tot * 2);
   } else {
-    // m-slabs: K > 1 overlaps the exchange of one slab with the Legendre work of the next.  Measured on
-    // 2 and 8 B200 at nside 4096 (profiles/r01_scaling_slabs.md) the exchange is 3-8 % of a transform
-    // and the extra kernel tails of K = 2..8 cost more than the overlap hides, so the default is 1.
-    const char* ek = getenv("HPSHT_NSLAB");
-    K = ek ? std::max(1, atoi(ek)) : 1;
-    K = (int)std::min<int64_t>(K, nm_loc);
+    // the per-destination blocks of the reference's all-to-all (src/sht.jl:20-32), all components in one
     aoff.assign((size_t)P + 1, 0);
     boff.assign((size_t)P + 1, 0);
     for (int t = 0; t < P; ++t) {
@@ -262,51 +243,44 @@ void hpsht_plan::ensure_stages() {
         lay.nr[(size_t)s] = nr_of[(size_t)t];
         lay.j[(size_t)s] = j;
       }
-    lay.sstart.resize((size_t)nm_loc);
-    lay.nms.resize((size_t)nm_loc);
-    for (int sl = 0; sl < K; ++sl)
-      for (int64_t i = slab_start(rank, sl); i < slab_start(rank, sl) + slab_size(rank, sl); ++i) {
-        lay.sstart[(size_t)i] = slab_start(rank, sl);
-        lay.nms[(size_t)i] = slab_size(rank, sl);
-      }
-    lay.ncs = max_ncomp;
     almside.alloc((size_t)aoff[(size_t)P] * 2);
     mapside.alloc((size_t)boff[(size_t)P] * 2);
     legF.alloc((size_t)max_ncomp * nr_loc * nm_tot * 2);
     d_boff.upload(boff.data(), boff.size(), stream);
-    // exchange (and the per-block FFT stream) outrank the Legendre stream: their few CTAs must not queue
+    // exchange and the per-block FFT stream outrank the Legendre stream: their few CTAs must not queue
     // behind the thousands of pending CTAs of the next Legendre launch
-    int prio_lo = 0, prio_hi = 0;
-    HP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     HP_CUDA(cudaStreamCreateWithPriority(&cstream, cudaStreamNonBlocking, prio_hi));
-    ev_slab.resize((size_t)K);
-    for (auto& e : ev_slab) HP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ev_done.resize((size_t)K);
-    for (auto& e : ev_done) HP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    sstream.resize((size_t)K);
-    for (auto& st : sstream) HP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    HP_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
   }
+  HP_CUDA(cudaStreamCreateWithPriority(&fstream, cudaStreamNonBlocking, prio_hi));
+  HP_CUDA(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
+  HP_CUDA(cudaStreamCreateWithFlags(&ostream, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&ev_hdone, &ev_a0, &ev_a1, &ev_entry, &ev_user, &ev_done})
+    HP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   leg.setup(lmax, mval.data(), mstart.data(), nm_loc, nr_tot, thetatot.data(), lay, max_ncomp, stream);
-  HP_REQUIRE(P == 1 || leg.nslabs() == K, HPSHT_ERR_INTERNAL, "slab count mismatch");
   fft.setup(nr_loc, nphi.data(), phi0.data(), rstart.data(), nm_tot, stream);
   setup_blocks();
+  for (auto* v : {&ev_blk, &ev_x, &ev_f}) {
+    v->resize((size_t)std::max(HB, 1));
+    for (auto& e : *v) HP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   HP_CUDA(cudaStreamSynchronize(stream));
   stages_ready = true;
 }
 
-
 // Host-pointer calls move 8 B per pixel and component over PCIe, ~0.4x the time the transform itself
-// needs at nside 4096.  With the ring pairs cut into HB tile-aligned blocks the copy of one block
-// overlaps the Legendre + exchange + FFT work of the others (HPSHT_HOST_BLOCKS, 1 = off).  The blocks
-// are ranges of the global pole -> equator pair list; with round-robin ring ownership every rank's
-// share of a block is a contiguous range [blo, bhi) of its local rings.
+// needs at nside 4096, and on P > 1 ranks every transform has the leg exchange in the middle.  With the
+// ring pairs cut into HB tile-aligned blocks the copy / exchange / FFT of one block overlaps the Legendre
+// work of the others (HPSHT_HOST_BLOCKS, 1 = off).  The blocks are ranges of the global pole -> equator
+// pair list; with round-robin ring ownership every rank's share of a block is a contiguous range
+// [blo, bhi) of its local rings.  Everything that decides HB is the same on every rank (the ranks of a
+// collective call must cut the same blocks): nside, P and the environment.
 void hpsht_plan::setup_blocks() {
   HB = 1;
   const char* eb = getenv("HPSHT_HOST_BLOCKS");
   int want = eb ? std::max(1, atoi(eb)) : (P <= 2 ? 6 : 4);
-  if (!eb && npix_loc < (1 << 22)) want = 1;  // small maps: the copies are microseconds
-  if (K != 1) want = 1;
+  if (!eb && 12 * nside * nside / P < (1 << 22)) want = 1;  // small maps: the copies are microseconds
+  const char* ed = getenv("HPSHT_DEV_BLOCKS");
+  dev_blocks = ed ? atoi(ed) != 0 : true;
   std::vector<double> w((size_t)nr_tot);
   {
     std::vector<int64_t> tot = rr_rindexes_tot(2 * nside, P);
@@ -321,7 +295,7 @@ void hpsht_plan::setup_blocks() {
   bool ok = true;
   for (int b = 0; b < HB && ok; ++b) {
     std::vector<int64_t> lo((size_t)P, INT64_MAX), hi((size_t)P, -1), cnt((size_t)P, 0);
-    for (int64_t slot : leg.block_slot_list(b)) {
+    for (int64_t slot : leg.block_slot_list(1, b)) {
       const int t = (int)(std::upper_bound(roff.begin(), roff.end(), slot) - roff.begin()) - 1;
       const int64_t j = slot - roff[(size_t)t];
       lo[(size_t)t] = std::min(lo[(size_t)t], j);
@@ -330,11 +304,11 @@ void hpsht_plan::setup_blocks() {
     }
     for (int t = 0; t < P; ++t) {
       if (cnt[(size_t)t] == 0) {  // no ring of this rank in the block: empty range at the running boundary
-        lo[(size_t)t] = hi[(size_t)t] = b == 0 ? nr_of[(size_t)t] : blo(b - 1, t);
+        lo[(size_t)t] = hi[(size_t)t] = b == 0 ? nr_of[(size_t)t] : blo(1, b - 1, t);
       }
       // blocks run pole -> equator = towards lower local ring indices, without gaps
       ok = ok && cnt[(size_t)t] == hi[(size_t)t] - lo[(size_t)t] &&
-           hi[(size_t)t] == (b == 0 ? nr_of[(size_t)t] : blo(b - 1, t));
+           hi[(size_t)t] == (b == 0 ? nr_of[(size_t)t] : blo(1, b - 1, t));
       bj_lo[(size_t)b * P + t] = lo[(size_t)t];
       bj_hi[(size_t)b * P + t] = hi[(size_t)t];
     }
@@ -347,49 +321,43 @@ void hpsht_plan::setup_blocks() {
   }
   fftb.clear();
   for (int b = 0; b < HB; ++b) {
-    const int64_t lo = blo(b, rank), hi = bhi(b, rank);
+    const int64_t lo = blo(1, b, rank), hi = bhi(1, b, rank);
     fftb.emplace_back(new RingFFT());
     if (hi > lo)
       fftb.back()->setup(hi - lo, nphi.data() + lo, phi0.data() + lo, rstart.data() + lo, nm_tot, stream, lo, nr_loc);
   }
-  for (auto* v : {&ev_blk, &ev_x, &ev_f}) {
-    v->resize((size_t)HB);
-    for (auto& e : *v) HP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  }
-  HP_CUDA(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
-  int prio_lo = 0, prio_hi = 0;
-  HP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  HP_CUDA(cudaStreamCreateWithPriority(&fstream, cudaStreamNonBlocking, prio_hi));
-  HP_CUDA(cudaEventCreateWithFlags(&ev_hdone, cudaEventDisableTiming));
-  HP_CUDA(cudaEventCreateWithFlags(&ev_a0, cudaEventDisableTiming));
-  HP_CUDA(cudaEventCreateWithFlags(&ev_a1, cudaEventDisableTiming));
 }
 
-// the leg pieces of ring block b: per peer and component one contiguous run of rows on both sides
-void hpsht_plan::exchange_block(bool synthesis, int ncomp, int b, cudaStream_t st) {
+// m-sharded <-> ring-sharded transpose of the leg array (communicate_alm2map! / communicate_map2alm!,
+// src/sht.jl:5-44,106-135) for the rings of one block: per peer and component one contiguous run of rows
+// on both sides, all of them in one grouped NCCL send/recv exchange.
+void hpsht_plan::exchange_block(bool synthesis, int ncomp, int set, int b, cudaStream_t st) {
   NcclApi& N = NcclApi::get();
   double* A = almside.p;
   double* B = mapside.p;
-  const int64_t mlo = blo(b, rank), mhi = bhi(b, rank);
+  const int64_t mlo = blo(set, b, rank), mhi = bhi(set, b, rank);
   HP_NCCL(N.GroupStart());
-  for (int t = 0; t < P; ++t) {
+  ncclResult_t err = ncclSuccess;
+  for (int t = 0; t < P && err == ncclSuccess; ++t) {
     if (t == rank) continue;
-    for (int c = 0; c < ncomp; ++c) {
+    for (int c = 0; c < ncomp && err == ncclSuccess; ++c) {
       // alm-side: my m's x t's rings of the block ; map-side: t's m's x my rings of the block
-      const size_t na = (size_t)(bhi(b, t) - blo(b, t)) * nm_loc * 2;
+      const size_t na = (size_t)(bhi(set, b, t) - blo(set, b, t)) * nm_loc * 2;
       const size_t nb = (size_t)(mhi - mlo) * nm_of[(size_t)t] * 2;
-      double* pa = A + ((size_t)aoff[(size_t)t] + ((size_t)c * nr_of[(size_t)t] + blo(b, t)) * nm_loc) * 2;
+      double* pa = A + ((size_t)aoff[(size_t)t] + ((size_t)c * nr_of[(size_t)t] + blo(set, b, t)) * nm_loc) * 2;
       double* pb = B + ((size_t)boff[(size_t)t] + ((size_t)c * nr_loc + mlo) * nm_of[(size_t)t]) * 2;
       if (synthesis) {
-        if (na) HP_NCCL(N.Send(pa, na, ncclDouble, t, comm, st));
-        if (nb) HP_NCCL(N.Recv(pb, nb, ncclDouble, t, comm, st));
+        if (na) err = N.Send(pa, na, ncclDouble, t, comm, st);
+        if (nb && err == ncclSuccess) err = N.Recv(pb, nb, ncclDouble, t, comm, st);
       } else {
-        if (nb) HP_NCCL(N.Send(pb, nb, ncclDouble, t, comm, st));
-        if (na) HP_NCCL(N.Recv(pa, na, ncclDouble, t, comm, st));
+        if (nb) err = N.Send(pb, nb, ncclDouble, t, comm, st);
+        if (na && err == ncclSuccess) err = N.Recv(pa, na, ncclDouble, t, comm, st);
       }
     }
   }
-  HP_NCCL(N.GroupEnd());
+  const ncclResult_t end = N.GroupEnd();  // always close the group, also on the error path
+  HP_NCCL(err);
+  HP_NCCL(end);
   if (mhi > mlo)
     for (int c = 0; c < ncomp; ++c) {  // own block never leaves the device
       const size_t n = (size_t)(mhi - mlo) * nm_loc * 2;
@@ -400,94 +368,63 @@ void hpsht_plan::exchange_block(bool synthesis, int ncomp, int b, cudaStream_t s
     }
 }
 
-// m-sharded <-> ring-sharded transpose of the leg array (communicate_alm2map! / communicate_map2alm!,
-// src/sht.jl:5-44,106-135), one m-slab at a time: all components of the slab in one grouped NCCL
-// send/recv exchange.  Per peer t the slab piece is contiguous on both sides.
-void hpsht_plan::exchange_slab(bool synthesis, int ncomp, int slab, cudaStream_t st) {
-  NcclApi& N = NcclApi::get();
-  double* A = almside.p;
-  double* B = mapside.p;
-  const int64_t my_ss = slab_start(rank, slab), my_ns = slab_size(rank, slab);
-  HP_NCCL(N.GroupStart());
-  for (int t = 0; t < P; ++t) {
-    if (t == rank) continue;
-    // alm-side: my m-slab x t's rings ; map-side: t's m-slab x my rings
-    const size_t na = (size_t)ncomp * nr_of[(size_t)t] * my_ns * 2;
-    const size_t nb = (size_t)ncomp * nr_loc * slab_size(t, slab) * 2;
-    double* pa = A + ((size_t)aoff[(size_t)t] + (size_t)max_ncomp * nr_of[(size_t)t] * my_ss) * 2;
-    double* pb = B + ((size_t)boff[(size_t)t] + (size_t)max_ncomp * nr_loc * slab_start(t, slab)) * 2;
-    if (synthesis) {
-      if (na) HP_NCCL(N.Send(pa, na, ncclDouble, t, comm, st));
-      if (nb) HP_NCCL(N.Recv(pb, nb, ncclDouble, t, comm, st));
-    } else {
-      if (nb) HP_NCCL(N.Send(pb, nb, ncclDouble, t, comm, st));
-      if (na) HP_NCCL(N.Recv(pa, na, ncclDouble, t, comm, st));
-    }
-  }
-  HP_NCCL(N.GroupEnd());
-  if (my_ns > 0) {  // own block never leaves the device
-    const size_t n = (size_t)ncomp * nr_loc * my_ns * 2;
-    double* pa = A + ((size_t)aoff[(size_t)rank] + (size_t)max_ncomp * nr_loc * my_ss) * 2;
-    double* pb = B + ((size_t)boff[(size_t)rank] + (size_t)max_ncomp * nr_loc * my_ss) * 2;
-    HP_CUDA(cudaMemcpyAsync(synthesis ? pb : pa, synthesis ? pa : pb, n * sizeof(double),
-                            cudaMemcpyDeviceToDevice, st));
-  }
-}
-
-void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
+// One transform.  The work is cut into the ring blocks of block set `set` (set 0: one block = everything):
+//   synthesis:  Legendre(b) -> [P>1: exchange(b) -> unpack(b)] -> ring FFT(b) -> [host map: D2H copy(b)]
+//   adjoint:    [host map: H2D copy(b)] -> ring FFT(b) -> [P>1: pack(b) -> exchange(b)] -> Legendre(b)
+// each stage on its own stream, so block b's exchange / FFT / copy run behind the Legendre kernels of the
+// next block.  All ranks of a P > 1 plan take the same path whatever kind of pointer they pass.
+void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp, bool async, cudaStream_t user) {
   HP_REQUIRE(ncomp == 1 || ncomp == 2, HPSHT_ERR_ARG, "Number of components must be 1 (spin 0) or 2 (spin 2).");
   HP_REQUIRE(ncomp <= max_ncomp, HPSHT_ERR_ARG, "plan was created with max_ncomp < ncomp");
   HP_REQUIRE(in && out, HPSHT_ERR_ARG, "null data pointer");
   HP_CUDA(cudaSetDevice(device));
   ensure_stages();
+  if (times_pending) finish_times();
   leg.reset_launches();
   fft.reset_launches();
   int64_t extra = 0;
   const size_t alm_d = (size_t)nalm_loc * ncomp * 2, map_d = (size_t)npix_loc * ncomp;
   const bool in_dev = is_device_pointer(in), out_dev = is_device_pointer(out);
-  // Device pointers: whoever produced `in` (or last touched `out`) did so on a stream this library does
-  // not know -- e.g. the caller's framework filling the buffer a moment ago -- while the plan works on its
-  // own non-blocking streams.  Wait for the device once on entry; on return the call is complete.
-  if (in_dev || out_dev) HP_CUDA(cudaDeviceSynchronize());
   if (!tm) tm.reset(new Timer());
   cudaEvent_t* e = tm->ev;
+  if (async) {
+    // stream-ordered form: the work is ordered after what the caller has queued on `user` so far, and `user`
+    // continues after it; nothing blocks the host
+    HP_REQUIRE(in_dev && out_dev, HPSHT_ERR_ARG, "the stream-ordered calls take device pointers only");
+    HP_CUDA(cudaEventRecord(ev_user, user));
+    HP_CUDA(cudaStreamWaitEvent(stream, ev_user, 0));
+  } else if (in_dev || out_dev) {
+    // Device pointers: whoever produced `in` (or last touched `out`) did so on a stream this library does
+    // not know -- e.g. the caller's framework filling the buffer a moment ago.  Wait for the device once on
+    // entry; on return the call is complete.  (hpsht_*_async takes the caller's stream instead.)
+    HP_CUDA(cudaDeviceSynchronize());
+  }
   HP_CUDA(cudaEventRecord(e[0], stream));
-  const double* d_in = in;
-  double* d_out = out;
-  // ring blocks are numbered pole -> equator = descending local pixels
-  auto blk_lo = [&](int b) { return pix_lo(b); };
-  auto blk_hi = [&](int b) { return pix_hi(b); };
-  const bool pipe_out = HB > 1 && synthesis && !out_dev;
-  const bool pipe_in = HB > 1 && !synthesis && !in_dev;
+  HP_CUDA(cudaEventRecord(ev_entry, stream));
+  for (cudaStream_t s : {cstream, fstream, hstream, ostream})
+    if (s) HP_CUDA(cudaStreamWaitEvent(s, ev_entry, 0));
+
+  const int spin = ncomp == 1 ? 0 : 2;
+  const bool host_map = synthesis ? !out_dev : !in_dev;  // the map side travels over PCIe
+  const int set = (HB > 1 && (P > 1 ? (dev_blocks || host_map) : host_map)) ? 1 : 0;
+  const int NB = leg.nblocks(set);
+  auto fftof = [&](int b) -> RingFFT& { return set ? *fftb[(size_t)b] : fft; };
+  auto plo = [&](int b) { return pix_at(blo(set, b, rank)); };
+  auto phi = [&](int b) { return pix_at(bhi(set, b, rank)); };
   // the first synthesis block / last adjoint block (the polar one) only touches the local m's
   // [0, mi_split): the rest of the alm copy overlaps that block's Legendre work
-  const int spin = ncomp == 1 ? 0 : 2;
-  const int mi_split = HB > 1 ? leg.block_mi_end(0, spin) : (int)nm_loc;
+  const int mi_split = NB > 1 ? leg.block_mi_end(set, 0, spin) : (int)nm_loc;
   const bool split_alm = mi_split > 0 && mi_split < (int)nm_loc && !getenv("HPSHT_NO_ALM_STREAM");
   // alm elements of the local m's [0, mi_split) form a prefix of every component
   const size_t a_split = split_alm ? (size_t)(mstart[(size_t)mi_split] + mval[(size_t)mi_split]) : 0;
-  const bool stream_alm_in = pipe_out && !in_dev && split_alm;
-  const bool stream_alm_out = pipe_in && !out_dev && split_alm;
-  if (pipe_in) {
-    stage_map.ensure(map_d);
-    d_in = stage_map.p;
-  } else if (stream_alm_in) {
-    stage_alm.ensure(alm_d);
-    d_in = stage_alm.p;
-    double* dst = stage_alm.p;
-    for (int part = 0; part < 2; ++part) {
-      for (int c = 0; c < ncomp; ++c) {
-        const size_t o = ((size_t)c * nalm_loc + (part ? a_split : 0)) * 2;
-        const size_t n = (part ? (size_t)nalm_loc - a_split : a_split) * 2;
-        HP_CUDA(cudaMemcpyAsync(dst + o, in + o, n * sizeof(double), cudaMemcpyHostToDevice, hstream));
-      }
-      HP_CUDA(cudaEventRecord(part ? ev_a1 : ev_a0, hstream));
-    }
-  } else if (!in_dev) {
+  const bool stream_alm_in = synthesis && !in_dev && split_alm;
+  const bool stream_alm_out = !synthesis && !out_dev && split_alm;
+
+  const double* d_in = in;
+  double* d_out = out;
+  if (!in_dev) {
     DevBuf<double>& sb = synthesis ? stage_alm : stage_map;
     sb.ensure(synthesis ? alm_d : map_d);
-    HP_CUDA(cudaMemcpyAsync(sb.p, in, (synthesis ? alm_d : map_d) * sizeof(double),
-                            cudaMemcpyHostToDevice, stream));
     d_in = sb.p;
   }
   if (!out_dev) {
@@ -495,148 +432,127 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
     sb.ensure(synthesis ? map_d : alm_d);
     d_out = sb.p;
   }
-  HP_CUDA(cudaEventRecord(e[1], stream));
   const int TB = 256;
   ExchGeom G;
   G.nm_tot = nm_tot;
   G.nr_loc = nr_loc;
   G.mmax = lmax;
   G.P = P;
-  G.K = K;
-  G.ncs = max_ncomp;
+  double* legA = P == 1 ? legF.p : almside.p;  // what the Legendre stage reads / writes
+
   if (synthesis) {
-    // alm2leg (src/sht.jl:85)
-    if (pipe_out) {
-      // all kernels first (a pageable destination makes cudaMemcpyAsync block the host), then the copies
-      double* legdst = P == 1 ? legF.p : almside.p;
-      leg.alm2leg_zero(legdst, P == 1 ? (int64_t)max_ncomp * nr_loc * nm_tot : aoff[(size_t)P], ncomp, stream);
-      if (stream_alm_in) {
-        HP_CUDA(cudaStreamWaitEvent(stream, ev_a0, 0));
-        leg.alm2leg_prep(d_in, nalm_loc, ncomp, 0, mi_split, stream);
-      } else {
-        leg.alm2leg_prep(d_in, nalm_loc, ncomp, 0, (int)nm_loc, stream);
-      }
-      if (P > 1) {
-        HP_CUDA(cudaEventRecord(ev_ready, stream));  // the stage buffers of the previous call are free again
-        HP_CUDA(cudaStreamWaitEvent(fstream, ev_ready, 0));
-      }
-      for (int b = 0; b < HB; ++b) {
-        if (b == 1 && stream_alm_in) {
-          HP_CUDA(cudaStreamWaitEvent(stream, ev_a1, 0));
-          leg.alm2leg_prep(d_in, nalm_loc, ncomp, mi_split, (int)nm_loc, stream);
+    // ---- alm in ----
+    if (stream_alm_in) {
+      for (int part = 0; part < 2; ++part) {
+        for (int c = 0; c < ncomp; ++c) {
+          const size_t o = ((size_t)c * nalm_loc + (part ? a_split : 0)) * 2;
+          const size_t n = (part ? (size_t)nalm_loc - a_split : a_split) * 2;
+          HP_CUDA(cudaMemcpyAsync(stage_alm.p + o, in + o, n * sizeof(double), cudaMemcpyHostToDevice, hstream));
         }
-        leg.alm2leg_block(b, legdst, ncomp, stream, b == HB - 1);
-        if (b == HB - 1) {
-          HP_CUDA(cudaEventRecord(e[2], stream));
-          HP_CUDA(cudaEventRecord(e[3], stream));
-        }
-        if (P == 1) {
-          fftb[(size_t)b]->leg2map(legF.p, d_out, npix_loc, ncomp, stream);
-          HP_CUDA(cudaEventRecord(ev_f[(size_t)b], stream));
-        } else {
-          // exchange of block b on the communication stream, unpack + ring FFT on the FFT stream
-          HP_CUDA(cudaEventRecord(ev_blk[(size_t)b], stream));
-          HP_CUDA(cudaStreamWaitEvent(cstream, ev_blk[(size_t)b], 0));
-          exchange_block(true, ncomp, b, cstream);
-          HP_CUDA(cudaEventRecord(ev_x[(size_t)b], cstream));
-          HP_CUDA(cudaStreamWaitEvent(fstream, ev_x[(size_t)b], 0));
-          const int64_t j0 = blo(b, rank), nj = bhi(b, rank) - j0;
-          if (nj > 0) {
-            dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nj));
-            k_unpack<<<grid, TB, 0, fstream>>>(reinterpret_cast<const double2*>(mapside.p), d_boff.p,
-                                               reinterpret_cast<double2*>(legF.p), G, j0, nj);
-            HP_CUDA(cudaGetLastError());
-            fftb[(size_t)b]->leg2map(legF.p, d_out, npix_loc, ncomp, fstream);
-            extra += 1;
-          }
-          extra += 1;
-          HP_CUDA(cudaEventRecord(ev_f[(size_t)b], fstream));
-        }
+        HP_CUDA(cudaEventRecord(part ? ev_a1 : ev_a0, hstream));
       }
-      HP_CUDA(cudaEventRecord(e[4], stream));
-      for (int b = 0; b < HB; ++b) {
-        HP_CUDA(cudaStreamWaitEvent(hstream, ev_f[(size_t)b], 0));
-        if (blk_hi(b) > blk_lo(b))
-          for (int c = 0; c < ncomp; ++c) {
-            const size_t o = (size_t)c * npix_loc + (size_t)blk_lo(b);
-            HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, (size_t)(blk_hi(b) - blk_lo(b)) * sizeof(double),
-                                    cudaMemcpyDeviceToHost, hstream));
-          }
-      }
-      HP_CUDA(cudaEventRecord(ev_hdone, hstream));
-      HP_CUDA(cudaStreamWaitEvent(stream, ev_hdone, 0));
-    } else if (P == 1) {
-      leg.alm2leg(d_in, nalm_loc, legF.p, (int64_t)max_ncomp * nr_loc * nm_tot, ncomp, stream);
-      HP_CUDA(cudaEventRecord(e[2], stream));
-      HP_CUDA(cudaEventRecord(e[3], stream));
+    } else if (!in_dev) {
+      HP_CUDA(cudaMemcpyAsync(stage_alm.p, in, alm_d * sizeof(double), cudaMemcpyHostToDevice, stream));
+    }
+    HP_CUDA(cudaEventRecord(e[1], stream));
+    // ---- alm2leg (src/sht.jl:85), block by block ----
+    leg.alm2leg_zero(legA, P == 1 ? (int64_t)max_ncomp * nr_loc * nm_tot : aoff[(size_t)P], ncomp, stream);
+    if (stream_alm_in) {
+      HP_CUDA(cudaStreamWaitEvent(stream, ev_a0, 0));
+      leg.alm2leg_prep(d_in, nalm_loc, ncomp, 0, mi_split, stream);
     } else {
-      // slab s is exchanged on the communication stream while slab s+1 is computed (src/sht.jl:90)
-      leg.alm2leg_begin(d_in, nalm_loc, almside.p, aoff[(size_t)P], ncomp, stream);
-      for (int s = 0; s < K; ++s) {
-        leg.alm2leg_slab(s, almside.p, ncomp, stream);
-        HP_CUDA(cudaEventRecord(ev_slab[(size_t)s], stream));
-        HP_CUDA(cudaStreamWaitEvent(cstream, ev_slab[(size_t)s], 0));
-        exchange_slab(true, ncomp, s, cstream);
+      leg.alm2leg_prep(d_in, nalm_loc, ncomp, 0, (int)nm_loc, stream);
+    }
+    for (int b = 0; b < NB; ++b) {
+      if (b == 1 && stream_alm_in) {
+        HP_CUDA(cudaStreamWaitEvent(stream, ev_a1, 0));
+        leg.alm2leg_prep(d_in, nalm_loc, ncomp, mi_split, (int)nm_loc, stream);
       }
-      HP_CUDA(cudaEventRecord(e[2], stream));  // end of the Legendre kernels
-      HP_CUDA(cudaEventRecord(ev_ready, cstream));
-      HP_CUDA(cudaStreamWaitEvent(stream, ev_ready, 0));
-      dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nr_loc));
-      k_unpack<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(mapside.p), d_boff.p,
-                                        reinterpret_cast<double2*>(legF.p), G, 0, nr_loc);
-      HP_CUDA(cudaGetLastError());
-      extra += 1 + K;
-      HP_CUDA(cudaEventRecord(e[3], stream));  // exposed (non-overlapped) exchange tail + unpack
+      leg.alm2leg_block(set, b, legA, ncomp, stream, b == NB - 1);
+      if (b == NB - 1) HP_CUDA(cudaEventRecord(e[2], stream));
+      const int64_t j0 = blo(set, b, rank), nj = bhi(set, b, rank) - j0;
+      if (P == 1) {
+        if (b == NB - 1) HP_CUDA(cudaEventRecord(e[3], stream));
+        fftof(b).leg2map(legF.p, d_out, npix_loc, ncomp, stream);  // leg2map (src/sht.jl:93)
+        HP_CUDA(cudaEventRecord(ev_f[(size_t)b], stream));
+        if (b == NB - 1) HP_CUDA(cudaEventRecord(e[4], stream));
+      } else {
+        // exchange of block b on the communication stream (src/sht.jl:90), unpack + ring FFT on the FFT stream
+        HP_CUDA(cudaEventRecord(ev_blk[(size_t)b], stream));
+        HP_CUDA(cudaStreamWaitEvent(cstream, ev_blk[(size_t)b], 0));
+        exchange_block(true, ncomp, set, b, cstream);
+        HP_CUDA(cudaEventRecord(ev_x[(size_t)b], cstream));
+        HP_CUDA(cudaStreamWaitEvent(fstream, ev_x[(size_t)b], 0));
+        extra += 1;
+        if (nj > 0) {
+          dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nj));
+          k_unpack<<<grid, TB, 0, fstream>>>(reinterpret_cast<const double2*>(mapside.p), d_boff.p,
+                                             reinterpret_cast<double2*>(legF.p), G, j0, nj);
+          HP_CUDA(cudaGetLastError());
+          extra += 1;
+        }
+        if (b == NB - 1) HP_CUDA(cudaEventRecord(e[3], fstream));
+        if (nj > 0) fftof(b).leg2map(legF.p, d_out, npix_loc, ncomp, fstream);
+        HP_CUDA(cudaEventRecord(ev_f[(size_t)b], fstream));
+        if (b == NB - 1) HP_CUDA(cudaEventRecord(e[4], fstream));
+      }
     }
-    // leg2map (src/sht.jl:93)
-    if (!pipe_out) {
-      fft.leg2map(legF.p, d_out, npix_loc, ncomp, stream);
-      HP_CUDA(cudaEventRecord(e[4], stream));
+    // ---- map out ----
+    if (!out_dev) {
+      for (int b = 0; b < NB; ++b) {
+        HP_CUDA(cudaStreamWaitEvent(ostream, ev_f[(size_t)b], 0));
+        if (phi(b) > plo(b))
+          for (int c = 0; c < ncomp; ++c) {
+            const size_t o = (size_t)c * npix_loc + (size_t)plo(b);
+            HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, (size_t)(phi(b) - plo(b)) * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ostream));
+          }
+      }
+      HP_CUDA(cudaEventRecord(ev_hdone, ostream));
+      HP_CUDA(cudaStreamWaitEvent(stream, ev_hdone, 0));
+    } else if (P > 1) {
+      for (int b = 0; b < NB; ++b) HP_CUDA(cudaStreamWaitEvent(stream, ev_f[(size_t)b], 0));
     }
-  } else if (pipe_in) {
-    // block b: host-to-device copy on the copy stream, then map2leg (+ pack and exchange when P > 1) and
-    // leg2alm of that block; the small equator-most blocks go first so that the compute starts early
-    leg.leg2alm_blocks_begin(ncomp, stream);
-    if (P > 1) {
-      HP_CUDA(cudaEventRecord(ev_ready, stream));
-      HP_CUDA(cudaStreamWaitEvent(fstream, ev_ready, 0));
-    }
-    // the local m's >= mi_split are complete before the last (polar) block starts: post-process them on
-    // the compute stream right there (a ~1 ms kernel) and copy them out on the copy stream while that block
-    // computes
+  } else {
+    HP_CUDA(cudaEventRecord(e[1], stream));
+    leg.leg2alm_begin(ncomp, stream);
+    // the local m's >= mi_split are complete before the last (polar) block starts: post-process them on the
+    // compute stream right there (a ~1 ms kernel) and copy them out while that block computes
     auto early_alm_out = [&]() {
-      leg.leg2alm_blocks_end(d_out, nalm_loc, ncomp, stream, mi_split, (int)nm_loc);
+      leg.leg2alm_end(d_out, nalm_loc, ncomp, stream, mi_split, (int)nm_loc);
       HP_CUDA(cudaEventRecord(ev_a1, stream));
-      HP_CUDA(cudaStreamWaitEvent(hstream, ev_a1, 0));
+      HP_CUDA(cudaStreamWaitEvent(ostream, ev_a1, 0));
       for (int c = 0; c < ncomp; ++c) {
         const size_t o = ((size_t)c * nalm_loc + a_split) * 2;
         HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, ((size_t)nalm_loc - a_split) * 2 * sizeof(double),
-                                cudaMemcpyDeviceToHost, hstream));
+                                cudaMemcpyDeviceToHost, ostream));
       }
-      HP_CUDA(cudaEventRecord(ev_hdone, hstream));
+      HP_CUDA(cudaEventRecord(ev_hdone, ostream));
     };
-    for (int b = HB - 1; b >= 0; --b) {
-      if (blk_hi(b) > blk_lo(b))
-        for (int c = 0; c < ncomp; ++c) {
-          const size_t o = (size_t)c * npix_loc + (size_t)blk_lo(b);
-          HP_CUDA(cudaMemcpyAsync(stage_map.p + o, in + o, (size_t)(blk_hi(b) - blk_lo(b)) * sizeof(double),
-                                  cudaMemcpyHostToDevice, hstream));
-        }
-      HP_CUDA(cudaEventRecord(ev_blk[(size_t)b], hstream));
+    // the small equator-most blocks go first so that the compute starts early
+    for (int b = NB - 1; b >= 0; --b) {
+      if (!in_dev) {
+        if (phi(b) > plo(b))
+          for (int c = 0; c < ncomp; ++c) {
+            const size_t o = (size_t)c * npix_loc + (size_t)plo(b);
+            HP_CUDA(cudaMemcpyAsync(stage_map.p + o, in + o, (size_t)(phi(b) - plo(b)) * sizeof(double),
+                                    cudaMemcpyHostToDevice, hstream));
+          }
+        HP_CUDA(cudaEventRecord(ev_blk[(size_t)b], hstream));
+      }
+      const int64_t j0 = blo(set, b, rank), nj = bhi(set, b, rank) - j0;
       if (P == 1) {
-        HP_CUDA(cudaStreamWaitEvent(stream, ev_blk[(size_t)b], 0));
-        fftb[(size_t)b]->map2leg(d_in, npix_loc, legF.p, ncomp, stream);
-        if (b == HB - 1) {
+        if (!in_dev) HP_CUDA(cudaStreamWaitEvent(stream, ev_blk[(size_t)b], 0));
+        fftof(b).map2leg(d_in, npix_loc, legF.p, ncomp, stream);  // map2leg (src/sht.jl:169)
+        if (b == NB - 1) {
           HP_CUDA(cudaEventRecord(e[2], stream));
           HP_CUDA(cudaEventRecord(e[3], stream));
         }
-        if (b == 0 && stream_alm_out) early_alm_out();
-        leg.leg2alm_block(b, legF.p, ncomp, stream, b == 0);
       } else {
-        HP_CUDA(cudaStreamWaitEvent(fstream, ev_blk[(size_t)b], 0));
-        const int64_t j0 = blo(b, rank), nj = bhi(b, rank) - j0;
+        if (!in_dev) HP_CUDA(cudaStreamWaitEvent(fstream, ev_blk[(size_t)b], 0));
+        if (nj > 0) fftof(b).map2leg(d_in, npix_loc, legF.p, ncomp, fstream);
+        if (b == NB - 1) HP_CUDA(cudaEventRecord(e[2], fstream));
         if (nj > 0) {
-          fftb[(size_t)b]->map2leg(d_in, npix_loc, legF.p, ncomp, fstream);
           dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nj));
           k_pack<<<grid, TB, 0, fstream>>>(reinterpret_cast<const double2*>(legF.p), d_boff.p,
                                            reinterpret_cast<double2*>(mapside.p), G, j0, nj);
@@ -645,96 +561,77 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp) {
         }
         HP_CUDA(cudaEventRecord(ev_f[(size_t)b], fstream));
         HP_CUDA(cudaStreamWaitEvent(cstream, ev_f[(size_t)b], 0));
-        exchange_block(false, ncomp, b, cstream);
+        exchange_block(false, ncomp, set, b, cstream);  // src/sht.jl:174
         extra += 1;
         HP_CUDA(cudaEventRecord(ev_x[(size_t)b], cstream));
+        if (b == NB - 1) HP_CUDA(cudaEventRecord(e[3], cstream));
         HP_CUDA(cudaStreamWaitEvent(stream, ev_x[(size_t)b], 0));
-        if (b == HB - 1) {
-          HP_CUDA(cudaEventRecord(e[2], stream));
-          HP_CUDA(cudaEventRecord(e[3], stream));
-        }
-        if (b == 0 && stream_alm_out) early_alm_out();
-        leg.leg2alm_block(b, almside.p, ncomp, stream, b == 0);
       }
+      if (b == 0 && stream_alm_out) early_alm_out();
+      leg.leg2alm_block(set, b, legA, ncomp, stream, b == 0);  // leg2alm (src/sht.jl:178)
     }
-    leg.leg2alm_blocks_end(d_out, nalm_loc, ncomp, stream, 0, stream_alm_out ? mi_split : (int)nm_loc);
+    leg.leg2alm_end(d_out, nalm_loc, ncomp, stream, 0, stream_alm_out ? mi_split : (int)nm_loc);
     HP_CUDA(cudaEventRecord(e[4], stream));
-  } else {
-    // map2leg (src/sht.jl:169)
-    fft.map2leg(d_in, npix_loc, legF.p, ncomp, stream);
-    HP_CUDA(cudaEventRecord(e[2], stream));
-    if (P == 1) {
-      HP_CUDA(cudaEventRecord(e[3], stream));
-      leg.leg2alm(legF.p, d_out, nalm_loc, ncomp, stream);  // src/sht.jl:178
-    } else {
-      dim3 grid((unsigned)((nm_tot + TB - 1) / TB), (unsigned)(ncomp * nr_loc));
-      k_pack<<<grid, TB, 0, stream>>>(reinterpret_cast<const double2*>(legF.p), d_boff.p,
-                                      reinterpret_cast<double2*>(mapside.p), G, 0, nr_loc);
-      HP_CUDA(cudaGetLastError());
-      extra += 1 + K;
-      HP_CUDA(cudaEventRecord(ev_ready, stream));
-      HP_CUDA(cudaStreamWaitEvent(cstream, ev_ready, 0));
-      leg.leg2alm_begin(ncomp, stream);
-      for (int s = 0; s < K; ++s) {  // src/sht.jl:174, slab by slab
-        exchange_slab(false, ncomp, s, cstream);
-        HP_CUDA(cudaEventRecord(ev_slab[(size_t)s], cstream));
+    // ---- alm out ----
+    if (stream_alm_out) {
+      for (int c = 0; c < ncomp; ++c) {
+        const size_t o = (size_t)c * nalm_loc * 2;
+        HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, a_split * 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
       }
-      // every slab's kernel starts as soon as its data has landed; the slab kernels run on their own
-      // streams so that the tail of one slab overlaps the head of the next
-      HP_CUDA(cudaEventRecord(ev_ready, stream));  // leg2alm_begin (buffer setup) done
-      for (int s = 0; s < K; ++s) {
-        cudaStream_t st = sstream[(size_t)s];
-        HP_CUDA(cudaStreamWaitEvent(st, ev_ready, 0));
-        HP_CUDA(cudaStreamWaitEvent(st, ev_slab[(size_t)s], 0));
-        leg.leg2alm_slab(s, almside.p, ncomp, st);
-        HP_CUDA(cudaEventRecord(ev_done[(size_t)s], st));
-      }
-      HP_CUDA(cudaStreamWaitEvent(stream, ev_slab[0], 0));
-      HP_CUDA(cudaEventRecord(e[3], stream));  // exposed exchange: pack + first slab
-      for (int s = 0; s < K; ++s) HP_CUDA(cudaStreamWaitEvent(stream, ev_done[(size_t)s], 0));
-      leg.mark_main_end(stream);
-      leg.leg2alm_end(d_out, nalm_loc, ncomp, stream);
+      HP_CUDA(cudaStreamWaitEvent(stream, ev_hdone, 0));
+    } else if (!out_dev) {
+      HP_CUDA(cudaMemcpyAsync(out, d_out, alm_d * sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
-    HP_CUDA(cudaEventRecord(e[4], stream));
-  }
-  if (stream_alm_out) {
-    for (int c = 0; c < ncomp; ++c) {
-      const size_t o = (size_t)c * nalm_loc * 2;
-      HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, a_split * 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    }
-    HP_CUDA(cudaStreamWaitEvent(stream, ev_hdone, 0));
-  } else if (!out_dev && !pipe_out) {
-    HP_CUDA(cudaMemcpyAsync(out, d_out, (synthesis ? map_d : alm_d) * sizeof(double),
-                            cudaMemcpyDeviceToHost, stream));
   }
   HP_CUDA(cudaEventRecord(e[5], stream));
-  HP_CUDA(cudaStreamSynchronize(stream));
-  if (cstream) HP_CUDA(cudaStreamSynchronize(cstream));
-  if (fstream) HP_CUDA(cudaStreamSynchronize(fstream));
-  if (hstream) HP_CUDA(cudaStreamSynchronize(hstream));
+  n_launch = leg.launches() + fft.launches() + extra;
+  for (auto& f : fftb) {
+    n_launch += f->launches();
+    f->reset_launches();
+  }
+  last_synthesis = synthesis;
+  times_pending = true;
+  if (async) {
+    HP_CUDA(cudaEventRecord(ev_done, stream));
+    HP_CUDA(cudaStreamWaitEvent(user, ev_done, 0));
+  } else {
+    synchronize();
+  }
+}
+
+void hpsht_plan::synchronize() {
+  HP_CUDA(cudaSetDevice(device));
+  for (cudaStream_t s : {stream, cstream, fstream, hstream, ostream})
+    if (s) HP_CUDA(cudaStreamSynchronize(s));
+  if (times_pending) finish_times();
+}
+
+void hpsht_plan::finish_times() {
+  times_pending = false;
+  if (!tm) return;
+  cudaEvent_t* e = tm->ev;
+  HP_CUDA(cudaEventSynchronize(e[5]));
   auto el = [&](int a, int b) {
     float f = 0;
-    cudaEventElapsedTime(&f, e[a], e[b]);
-    return (double)f;
+    if (cudaEventElapsedTime(&f, e[a], e[b]) != cudaSuccess) {
+      cudaGetLastError();
+      f = 0;
+    }
+    return (double)std::max(f, 0.f);
   };
   std::memset(ms, 0, sizeof(ms));
   ms[0] = el(0, 5);
   ms[5] = el(0, 1);
   ms[6] = el(4, 5);
   ms[3] = el(2, 3);
-  if (synthesis) {
+  if (last_synthesis) {
     ms[2] = el(1, 2);  // includes the O(nalm) prep kernel
     ms[4] = el(3, 4);
   } else {
     ms[4] = el(1, 2);
-    ms[2] = el(3, 4);  // includes reduce + post kernels
+    ms[2] = el(3, 4);  // includes the post kernel
   }
   ms[1] = leg.main_kernel_ms();
-  n_launch = leg.launches() + fft.launches() + extra;
-  for (auto& f : fftb) {
-    n_launch += f->launches();
-    f->reset_launches();
-  }
 }
 
 // =================================================================================================
@@ -1109,26 +1006,15 @@ int hpsht_plan_destroy(hpsht_plan* plan) {
   return guarded([&] {
     if (!plan) return;
     cudaSetDevice(plan->device);
-    if (plan->stream) cudaStreamSynchronize(plan->stream);
+    for (cudaStream_t st : {plan->stream, plan->cstream, plan->fstream, plan->hstream, plan->ostream})
+      if (st) cudaStreamSynchronize(st);
     if (plan->comm) NcclApi::get().CommDestroy(plan->comm);
-    if (plan->cstream) cudaStreamSynchronize(plan->cstream);
-    for (auto& e : plan->ev_slab) cudaEventDestroy(e);
-    for (auto& e : plan->ev_done) cudaEventDestroy(e);
-    for (auto& st : plan->sstream) {
-      cudaStreamSynchronize(st);
-      cudaStreamDestroy(st);
-    }
-    if (plan->ev_ready) cudaEventDestroy(plan->ev_ready);
-    for (auto& e : plan->ev_blk) cudaEventDestroy(e);
-    for (auto& e : plan->ev_x) cudaEventDestroy(e);
-    for (auto& e : plan->ev_f) cudaEventDestroy(e);
-    if (plan->fstream) cudaStreamDestroy(plan->fstream);
-    if (plan->ev_a0) cudaEventDestroy(plan->ev_a0);
-    if (plan->ev_a1) cudaEventDestroy(plan->ev_a1);
-    if (plan->ev_hdone) cudaEventDestroy(plan->ev_hdone);
-    if (plan->hstream) cudaStreamDestroy(plan->hstream);
-    if (plan->cstream) cudaStreamDestroy(plan->cstream);
-    if (plan->stream) cudaStreamDestroy(plan->stream);
+    for (auto* v : {&plan->ev_blk, &plan->ev_x, &plan->ev_f})
+      for (auto& e : *v) cudaEventDestroy(e);
+    for (cudaEvent_t e : {plan->ev_hdone, plan->ev_a0, plan->ev_a1, plan->ev_entry, plan->ev_user, plan->ev_done})
+      if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : {plan->cstream, plan->fstream, plan->hstream, plan->ostream, plan->stream})
+      if (st) cudaStreamDestroy(st);
     delete plan;
   });
 }
@@ -1167,14 +1053,32 @@ int hpsht_plan_map_info(const hpsht_plan* plan, int64_t* rings, int64_t* rstart,
 int hpsht_alm2map(hpsht_plan* plan, const double* alm, double* map, int ncomp, int /*nthreads*/) {
   return guarded([&] {
     HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
-    plan->run(true, alm, map, ncomp);
+    plan->run(true, alm, map, ncomp, false, nullptr);
   });
 }
 int hpsht_adjoint_alm2map(hpsht_plan* plan, const double* map, double* alm, int ncomp,
                           int /*nthreads*/) {
   return guarded([&] {
     HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
-    plan->run(false, map, alm, ncomp);
+    plan->run(false, map, alm, ncomp, false, nullptr);
+  });
+}
+int hpsht_alm2map_async(hpsht_plan* plan, const double* d_alm, double* d_map, int ncomp, void* cuda_stream) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    plan->run(true, d_alm, d_map, ncomp, true, static_cast<cudaStream_t>(cuda_stream));
+  });
+}
+int hpsht_adjoint_alm2map_async(hpsht_plan* plan, const double* d_map, double* d_alm, int ncomp, void* cuda_stream) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    plan->run(false, d_map, d_alm, ncomp, true, static_cast<cudaStream_t>(cuda_stream));
+  });
+}
+int hpsht_plan_synchronize(hpsht_plan* plan) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    plan->synchronize();
   });
 }
 
@@ -1225,6 +1129,7 @@ int hpsht_plan_alm2cl(hpsht_plan* plan, const double* alm1, const double* alm2, 
 int hpsht_plan_timings(const hpsht_plan* plan, double ms[HPSHT_NTIMES]) {
   return guarded([&] {
     HP_REQUIRE(plan && ms, HPSHT_ERR_ARG, "null pointer");
+    if (plan->times_pending) const_cast<hpsht_plan*>(plan)->synchronize();
     std::memcpy(ms, plan->ms, sizeof(plan->ms));
   });
 }

@@ -27,9 +27,10 @@ struct NcclApi {
 
   static NcclApi& get() {
     static NcclApi api;
-    if (!api.handle) api.load();
+    if (!api.ready) api.load();
     return api;
   }
+  bool ready = false;   // every symbol resolved (a partial load leaves it false: the next get() tries again)
 
  private:
   void load() {
@@ -55,6 +56,7 @@ struct NcclApi {
     HP_SYM(GetErrorString, "ncclGetErrorString")
     HP_SYM(GetVersion, "ncclGetVersion")
 #undef HP_SYM
+    ready = true;
   }
 };
 

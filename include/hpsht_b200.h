@@ -150,6 +150,16 @@ int hpsht_alm2map(hpsht_plan* plan, const double* alm, double* map, int ncomp, i
 int hpsht_adjoint_alm2map(hpsht_plan* plan, const double* map, double* alm, int ncomp,
                           int nthreads);
 
+/* Stream-ordered forms for solver loops that keep DAlm / DMap resident on the device (device pointers
+   only): the transform is ordered after everything queued on `cuda_stream` (a cudaStream_t; NULL = the
+   legacy default stream) at the time of the call, `cuda_stream` continues after it, and the host is not
+   blocked.  Collective like the blocking forms.  hpsht_plan_synchronize waits for the plan's streams;
+   hpsht_plan_timings implies it.                                                         */
+int hpsht_alm2map_async(hpsht_plan* plan, const double* d_alm, double* d_map, int ncomp, void* cuda_stream);
+int hpsht_adjoint_alm2map_async(hpsht_plan* plan, const double* d_map, double* d_alm, int ncomp,
+                                void* cuda_stream);
+int hpsht_plan_synchronize(hpsht_plan* plan);
+
 /* ---- shards on the device: scatter / gather / algebra -------------------
    All collective over the plan's ranks; host or device pointers.  `ncomp` components are moved
    together ([ncomp][...] as in hpsht_alm2map).

@@ -1,8 +1,8 @@
 """FP64 CPU port of the hot path (TEST INFRASTRUCTURE / CPU BASELINE ONLY).
 
 Legendre stage: oracle/cpu_port.cpp (OpenMP, same formulation as the CUDA kernels).
-Ring-FFT stage: scipy.fft (pocketfft — the same FFT family ducc0 uses) with the alias fold /
-phase shift of SURVEY row A8/A9 in numpy.  Used by tests as a second, independent-in-precision
+Ring stage: oracle/cpu_port.cpp too (alias fold / phase shift of SURVEY rows A8/A9 + a plain mixed-radix /
+Bluestein FFT per ring, OpenMP over rings).  Used by tests as a second, independent-in-precision
 check of the formulation and by bench.py as the `cpu_baseline` / `--impl reference` arm
 ("kind": "port" — the real reference needs Julia + MPI + Ducc0, none of which exist here).
 """
@@ -12,7 +12,6 @@ import ctypes as C
 import os
 
 import numpy as np
-import scipy.fft
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -72,51 +71,39 @@ def leg2alm(leg, spin, lmax, mval, mstart0, theta, nalm):
     return alm
 
 
-def _phase(nm, phi0):
-    m = np.arange(nm, dtype=np.float64)
-    return np.exp(1j * m * phi0)
+def max_threads():
+    """OpenMP threads the port will actually use (honours OMP_NUM_THREADS / set_threads)."""
+    f = lib().cpu_max_threads
+    f.restype = C.c_int
+    return int(f())
 
 
-def fold(leg_row, phi0, n):
-    """half-complex spectrum of one ring from its leg row (SURVEY A8 fold rule)."""
-    nm = len(leg_row)
-    t = leg_row * _phase(nm, phi0)
-    hc = np.zeros(n // 2 + 1, dtype=np.complex128)
-    hc[0] = t[0].real
-    m = np.arange(1, nm)
-    i1 = m % n
-    i2 = (n - i1) % n
-    s1 = i1 <= n // 2
-    np.add.at(hc, i1[s1], t[1:][s1])
-    s2 = i2 <= n // 2
-    np.add.at(hc, i2[s2], np.conj(t[1:][s2]))
-    return hc
+def set_threads(n):
+    lib().cpu_set_threads(C.c_int(int(n)))
 
 
 def leg2map(leg, nphi, phi0, rstart0, npix):
-    """leg [ncomp, nring, nm] -> map [ncomp, npix] float64 (src/sht.jl:93)."""
+    """leg [ncomp, nring, nm] -> map [ncomp, npix] float64 (src/sht.jl:93); OpenMP over rings."""
+    leg = np.ascontiguousarray(leg, dtype=np.complex128)
     ncomp, nring, nm = leg.shape
+    nphi = np.ascontiguousarray(nphi, dtype=i64)
+    phi0 = np.ascontiguousarray(phi0, dtype=np.float64)
+    rstart0 = np.ascontiguousarray(rstart0, dtype=i64)
     out = np.zeros((ncomp, npix), dtype=np.float64)
-    for c in range(ncomp):
-        for ir in range(nring):
-            n = int(nphi[ir])
-            hc = fold(leg[c, ir], phi0[ir], n)
-            out[c, rstart0[ir]:rstart0[ir] + n] = scipy.fft.irfft(hc, n) * n
+    lib().cpu_leg2map(C.c_int(ncomp), C.c_int64(nm), C.c_int64(nring), _p(nphi), _p(phi0), _p(rstart0),
+                      _p(leg), _p(out), C.c_int64(npix))
     return out
 
 
 def map2leg(mp, nm, nphi, phi0, rstart0):
-    """map [ncomp, npix] -> leg [ncomp, nring, nm] complex128 (src/sht.jl:169)."""
+    """map [ncomp, npix] -> leg [ncomp, nring, nm] complex128 (src/sht.jl:169); OpenMP over rings."""
+    mp = np.ascontiguousarray(mp, dtype=np.float64)
     ncomp = mp.shape[0]
+    nphi = np.ascontiguousarray(nphi, dtype=i64)
+    phi0 = np.ascontiguousarray(phi0, dtype=np.float64)
+    rstart0 = np.ascontiguousarray(rstart0, dtype=i64)
     nring = len(nphi)
     leg = np.zeros((ncomp, nring, nm), dtype=np.complex128)
-    m = np.arange(nm)
-    for c in range(ncomp):
-        for ir in range(nring):
-            n = int(nphi[ir])
-            X = scipy.fft.rfft(mp[c, rstart0[ir]:rstart0[ir] + n])
-            k = m % n
-            up = k > n // 2
-            v = np.where(up, np.conj(X[np.where(up, n - k, 0)]), X[np.where(up, 0, k)])
-            leg[c, ir] = v * np.conj(_phase(nm, phi0[ir]))
+    lib().cpu_map2leg(C.c_int(ncomp), C.c_int64(nm), C.c_int64(nring), _p(nphi), _p(phi0), _p(rstart0),
+                      _p(mp), C.c_int64(mp.shape[1]), _p(leg))
     return leg
