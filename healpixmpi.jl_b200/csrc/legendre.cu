@@ -1592,7 +1592,7 @@ void LegendreStage::alm2leg_zero(double* d_leg, int64_t leg_elems, int ncomp, cu
   ensure_spin(spin, stream);
   // (m, ring) combinations beyond mlim are never visited by a CTA: their leg is exactly 0
   HP_CUDA(cudaMemsetAsync(d_leg, 0, (size_t)leg_elems * 2 * sizeof(double), stream));
-  cudaEventRecord(ev0_, stream);
+  first_block_ = true;
 }
 
 // alm -> prepared per-step stream for the local m's [mi0, mi1)
@@ -1627,6 +1627,8 @@ void LegendreStage::alm2leg_block(int set, int b, double* d_leg, int ncomp, cuda
   P.leg = d_leg;
   auto count = [&](int kind) { return rg[(size_t)(b * LK_COUNT + kind) + 1] - rg[(size_t)(b * LK_COUNT + kind)]; };
   const bool side = count(LK_STD) > 0 && (count(LK_DP) > 0 || count(LK_DE) > 0);
+  if (first_block_) cudaEventRecord(ev0_, stream);
+  first_block_ = false;
   if (side) fork(stream);
   for (int kind : {LK_DP, LK_DE, LK_STD}) {
     const int n = count(kind);
@@ -1652,7 +1654,6 @@ void LegendreStage::alm2leg(const double* d_alm, int64_t alm_cstride, double* d_
                             int ncomp, cudaStream_t stream) {
   alm2leg_zero(d_leg, leg_elems, ncomp, stream);
   alm2leg_prep(d_alm, alm_cstride, ncomp, 0, (int)nm_, stream);
-  cudaEventRecord(ev0_, stream);
   alm2leg_block(0, 0, d_leg, ncomp, stream, true);
 }
 
@@ -1666,7 +1667,7 @@ void LegendreStage::leg2alm_begin(int ncomp, cudaStream_t stream) {
   d_part_.ensure(need);
   // every item adds to its row: start from zero
   if (need) HP_CUDA(cudaMemsetAsync(d_part_.p, 0, need * sizeof(double), stream));
-  cudaEventRecord(ev0_, stream);
+  first_block_ = true;
 }
 
 void LegendreStage::leg2alm_block(int set, int b, const double* d_leg, int ncomp, cudaStream_t stream, bool last) {
@@ -1680,6 +1681,8 @@ void LegendreStage::leg2alm_block(int set, int b, const double* d_leg, int ncomp
   // the polar launch has its own partial-sum rows and runs next to the other two, which share rows and
   // therefore follow each other on the caller's stream
   const bool side = count(LK_DP) > 0 && (count(LK_STD) > 0 || count(LK_DE) > 0);
+  if (first_block_) cudaEventRecord(ev0_, stream);
+  first_block_ = false;
   if (side) fork(stream);
   for (int kind : {LK_DP, LK_DE, LK_STD}) {
     const int n = count(kind);

@@ -108,6 +108,7 @@ class LegendreStage {
   bool have_[2] = {false, false};
   double culled0_ = 0, culled2_ = 0, dense_ = 0;
   int64_t launches_ = 0;
+  bool first_block_ = true;   // the next block launch is the first of its transform (timing event)
 
   // device: geometry
   DevBuf<double> d_cth_, d_sth_, d_sh_, d_ch_, d_x2_, d_s2_, d_ny2_;
