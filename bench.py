@@ -3,18 +3,23 @@
 
     python bench.py --gpus N --steps K --warmup W        (N>1: launched under torchrun, one rank/GPU)
 
-One STEP = the headline workload of BASELINE.json (configs[3]): spin-0 alm2map! + spin-0
-adjoint_alm2map! + spin-2 alm2map! + spin-2 adjoint_alm2map! at nside=4096, lmax=8191 on
-DAlm{RR}/DMap{RR} shards spread over the N ranks (strong scaling: the problem is fixed).
-It fits one B200 (about 12 GB), so N=1 runs the same workload.
+One STEP = the workload of one BASELINE.json config on DAlm{RR}/DMap{RR} shards spread over the N ranks
+(strong scaling: the problem is fixed).  Default = the headline, configs[3]: spin-0 alm2map! + spin-0
+adjoint_alm2map! + spin-2 alm2map! + spin-2 adjoint_alm2map! at nside=4096, lmax=8191 (fits one B200, so
+N=1 runs the same workload).  --config 2 | 3 | 5 selects the other GPU configs of BASELINE.json.
 
-  value       ms per step, shards resident in HBM when the timed region starts (CUDA events on the
-              plan's stream, max over ranks)
-  e2e         ms per step through the public API (alm2map_/adjoint_alm2map_ on DAlm/DMap) with HOST
-              (pinned) buffers: H2D of the inputs and D2H of the results inside the timed region
-  roofline    the Legendre kernel with the largest share of the step against the FP64 FMA pipe
+  value         ms per step, shards resident in HBM when the timed region starts (CUDA events on the plan's
+                stream, max over ranks)
+  e2e           ms per step through the public API (Plan.alm2map / Plan.adjoint_alm2map) with HOST (pinned)
+                buffers: H2D of the inputs and D2H of the results inside the timed region
+  roofline      the Legendre kernel with the largest share of the step against the FP64 FMA pipe;
+                roofline_fft: the ring-FFT stage against HBM; roofline_nvlink (N>1): the leg exchange
+                against NVLink -- the last two from a short extra pass with the stages run back to back
+                (in the timed region they overlap block by block)
+  parity        after the timed region: the adjointness identity <f, Y a> = <Y^T f, a>_w over all ranks, and
+                a sample of rank 0's rings of Y a against the long-double oracle (checker only)
   cpu_baseline  the FP64 OpenMP CPU port (oracle/cpu_port.*; kind "port": the real reference needs
-              Julia+MPI+Ducc0, absent here) timed on a bounded sample and extrapolated to the step
+                Julia+MPI+Ducc0, absent here) timed on a bounded sample of the same step
 
 --impl reference times that CPU port alone (rank 0 only) and prints the same JSON shape.
 Smaller problems for smoke runs: --nside/--lmax.
@@ -22,6 +27,7 @@ Smaller problems for smoke runs: --nside/--lmax.
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -35,6 +41,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "alm2map+adjoint ms and FP64 %peak at nside=4096 lmax=8191, 1/2/4/8 B200"
+
+# BASELINE.json configs -> (nside, lmax, [(ncomp, direction)])
+CONFIGS = {
+    2: (1024, 3071, [(1, "a2m"), (1, "adj")]),
+    3: (2048, 6143, [(1, "a2m"), (2, "a2m")]),
+    4: (4096, 8191, [(1, "a2m"), (1, "adj"), (2, "a2m"), (2, "adj")]),
+    5: (8192, 16383, [(1, "adj")]),
+}
+NVLINK_GBS = 900.0  # NVLink 5, per direction per GPU (B200_PROFILING.md)
 
 
 def log(*a):
@@ -123,66 +138,87 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline (port): bounded sample, extrapolated through the work model
+# CPU baseline (port): a bounded sample of the step, every stage in OpenMP C++
 # ------------------------------------------------------------------------------------------------
-def cpu_port_step_ms(nside, lmax, budget_s=20.0):
-    """Time the FP64 OpenMP port (Legendre: oracle/cpu_port.cpp; rings: scipy/pocketfft) on a sample of
-    the workload and extrapolate to one full step (spin-0 + spin-2, both directions)."""
-    from oracle import cpu_port as P
-    from oracle import oracle as O
+class CpuPort:
+    """The FP64 OpenMP port (oracle/cpu_port.cpp: Legendre recurrences + ring FFTs) on all host cores.  A step
+    is timed on every `stride`-th m (Legendre) and every `stride`-th ring (ring stage) and scaled by the work
+    model; stride 1 = the whole step, nothing extrapolated."""
 
-    cores = os.cpu_count() or 1
-    nr = 4 * nside - 1
-    rings = np.arange(1, nr + 1)
-    nphi, theta, phi0, fp = O.healpix_rings(nside, rings)
-    all_m = np.arange(lmax + 1)
-    mstart_all = O.rr_mstart1(lmax, 1, all_m) - 1
-    nalm = (lmax + 1) * (lmax + 2) // 2
-    rng = np.random.default_rng(0)
+    def __init__(self, nside, lmax, transforms):
+        from oracle import cpu_port as P
+        from oracle import oracle as O
 
-    def leg_time(spin, stride):
-        ncomp = 1 if spin == 0 else 2
-        mval = all_m[::stride]
-        alm = rng.standard_normal((ncomp, nalm)) + 1j * rng.standard_normal((ncomp, nalm))
+        self.P = P
+        self.nside, self.lmax, self.transforms = nside, lmax, transforms
+        # torchrun exports OMP_NUM_THREADS=1: ask for the machine explicitly and report what OpenMP grants
+        P.set_threads(os.cpu_count() or 1)
+        self.threads = P.max_threads()
+        nr = 4 * nside - 1
+        self.nr = nr
+        self.nphi, self.theta, self.phi0, _ = O.healpix_rings(nside, np.arange(1, nr + 1))
+        self.all_m = np.arange(lmax + 1)
+        self.mstart = O.rr_mstart1(lmax, 1, self.all_m) - 1
+        self.nalm = (lmax + 1) * (lmax + 2) // 2
+        self.full = {s: P.legendre_steps(s, lmax, self.all_m, self.theta)[0] for s in (0, 2)}
+        self.rng = np.random.default_rng(0)
+        self.rate = None  # spin-0 steps / s, calibrated once
+
+    def _calibrate(self):
+        mval = self.all_m[::max(1, (self.lmax + 1) // 16)]
+        alm = self.rng.standard_normal((1, self.nalm)) + 1j * self.rng.standard_normal((1, self.nalm))
         t0 = time.perf_counter()
-        leg = P.alm2leg(alm, spin, lmax, mval, mstart_all[mval], theta)
-        t1 = time.perf_counter()
-        P.leg2alm(leg, spin, lmax, mval, mstart_all[mval], theta, nalm)
-        t2 = time.perf_counter()
-        s_c, _ = P.legendre_steps(spin, lmax, mval, theta)
-        return (t1 - t0), (t2 - t1), s_c
+        self.P.alm2leg(alm, 0, self.lmax, mval, self.mstart[mval], self.theta)
+        dt = time.perf_counter() - t0
+        self.rate = self.P.legendre_steps(0, self.lmax, mval, self.theta)[0] / max(dt, 1e-9)
 
-    # calibrate on a sparse m-subset, then size the real sample for ~budget_s
-    stride = max(1, (lmax + 1) // 16)
-    a, b, s = leg_time(0, stride)
-    rate = s / max(a, 1e-9)
-    full0, _ = P.legendre_steps(0, lmax, all_m, theta)
-    full2, _ = P.legendre_steps(2, lmax, all_m, theta)
-    est_full = (full0 * 2 + full2 * 2 * 4.3) / rate
-    stride = int(max(1, np.ceil(est_full / (0.6 * budget_s))))
-    out = {}
-    tot_ms = 0.0
-    sample_steps = 0.0
-    for spin, full in ((0, full0), (2, full2)):
-        a, b, s = leg_time(spin, stride)
-        tot_ms += (a + b) * (full / s) * 1e3
-        sample_steps += 2 * s
-        out[f"legendre_spin{spin}_steps_per_s"] = s / a
-    # ring stage on a sample of rings, extrapolated by pixel count (spin 0: 1 comp, spin 2: 2 comps)
-    nsel = max(8, min(nr, int(nr * 0.02)))
-    sel = np.unique(np.linspace(0, nr - 1, nsel).astype(int))
-    rs0 = np.concatenate([[0], np.cumsum(nphi[sel])[:-1]])
-    leg = rng.standard_normal((1, len(sel), lmax + 1)) + 1j * rng.standard_normal((1, len(sel), lmax + 1))
-    t0 = time.perf_counter()
-    mp = P.leg2map(leg, nphi[sel], phi0[sel], rs0, int(nphi[sel].sum()))
-    P.map2leg(mp, lmax + 1, nphi[sel], phi0[sel], rs0)
-    t1 = time.perf_counter()
-    ring_ms = (t1 - t0) * (nr / len(sel)) * 3 * 1e3  # 3 components per step, both directions timed
-    tot_ms += ring_ms
-    sample = (f"Legendre: every {stride}-th m of 0..{lmax} x all {nr} rings, spin 0 and spin 2, both "
-              f"directions ({sample_steps:.3g} of {2 * (full0 + full2):.3g} steps), OpenMP {cores} threads; "
-              f"ring FFT: {len(sel)} of {nr} rings via scipy.fft (single thread); extrapolated to the full step")
-    return tot_ms, cores, sample, out
+    def stride_for(self, budget_s):
+        if self.rate is None:
+            self._calibrate()
+        est = sum(self.full[0 if c == 1 else 2] * (1.0 if c == 1 else 4.3) for c, _ in self.transforms) / self.rate
+        return int(max(1, np.ceil(1.15 * est / max(budget_s, 1e-3))))
+
+    def step_ms(self, stride):
+        P, lmax = self.P, self.lmax
+        mval = self.all_m[::stride]
+        rsel = np.arange(0, self.nr, stride)
+        nphi, phi0 = self.nphi[rsel], self.phi0[rsel]
+        rs0 = np.concatenate([[0], np.cumsum(nphi)[:-1]]).astype(np.int64)
+        npix = int(nphi.sum())
+        tot = leg_s = ring_s = 0.0
+        for ncomp, d in self.transforms:
+            spin = 0 if ncomp == 1 else 2
+            scale_m = self.full[spin] / P.legendre_steps(spin, lmax, mval, self.theta)[0]
+            scale_r = float(self.nphi.sum()) / npix
+            if d == "a2m":
+                alm = self.rng.standard_normal((ncomp, self.nalm)) + 1j * self.rng.standard_normal((ncomp, self.nalm))
+                t0 = time.perf_counter()
+                P.alm2leg(alm, spin, lmax, mval, self.mstart[mval], self.theta)
+                t1 = time.perf_counter()
+                legr = self.rng.standard_normal((ncomp, len(rsel), lmax + 1)) + 0j
+                t2 = time.perf_counter()
+                P.leg2map(legr, nphi, phi0, rs0, npix)
+                t3 = time.perf_counter()
+            else:
+                mp = self.rng.standard_normal((ncomp, npix))
+                t2 = time.perf_counter()
+                P.map2leg(mp, lmax + 1, nphi, phi0, rs0)
+                t3 = time.perf_counter()
+                leg = self.rng.standard_normal((ncomp, self.nr, len(mval))) + 0j
+                t0 = time.perf_counter()
+                P.leg2alm(leg, spin, lmax, mval, self.mstart[mval], self.theta, self.nalm)
+                t1 = time.perf_counter()
+            leg_s += (t1 - t0) * scale_m
+            ring_s += (t3 - t2) * scale_r
+        tot = (leg_s + ring_s) * 1e3
+        return tot, leg_s * 1e3, ring_s * 1e3
+
+    def describe(self, stride, leg_ms, ring_ms):
+        what = "the whole step, nothing extrapolated" if stride == 1 else (
+            f"every {stride}-th m (Legendre) and every {stride}-th ring (ring FFT) of the step, scaled by the "
+            f"work model (steps after the mlim cut / pixels)")
+        return (f"{what}; OpenMP {self.threads} threads (omp_get_max_threads; host has {os.cpu_count()} CPUs); "
+                f"Legendre {leg_ms:.0f} ms + ring stage {ring_ms:.0f} ms per step")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -192,11 +228,16 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nside", type=int, default=4096)
-    ap.add_argument("--lmax", type=int, default=8191)
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS))
+    ap.add_argument("--nside", type=int, default=None)
+    ap.add_argument("--lmax", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0,
+                    help="seconds of CPU work for the cpu_baseline sample of the default arm")
+    ap.add_argument("--ref-budget", type=float, default=150.0,
+                    help="seconds of CPU work for the whole --impl reference run (all steps)")
     args = ap.parse_args()
 
     # stdout carries exactly one JSON line: route everything else (NCCL banners, library chatter) to
@@ -213,30 +254,36 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    nside, lmax = args.nside, args.lmax
-    workload = (f"spin-0 + spin-2 alm2map!/adjoint_alm2map! nside={nside} lmax={lmax}, DAlm{{RR}}/DMap{{RR}} "
-                f"over {world} rank(s)")
-    config = {"workload": workload, "nside": nside, "lmax": lmax, "ranks": world,
+    nside, lmax, transforms = CONFIGS[args.config]
+    nside = args.nside or nside
+    lmax = args.lmax or lmax
+    tnames = ", ".join(f"spin-{0 if c == 1 else 2} {'alm2map!' if d == 'a2m' else 'adjoint_alm2map!'}" for c, d in transforms)
+    workload = f"BASELINE config {args.config}: {tnames} at nside={nside} lmax={lmax}, DAlm{{RR}}/DMap{{RR}} over {world} rank(s)"
+    config = {"workload": workload, "nside": nside, "lmax": lmax, "ranks": world, "baseline_config": args.config,
               "inputs": "counter-based N(0,1) alm / maps (Philox), larger than L2 (no flush needed)"}
+    metric = METRIC if args.config == 4 else f"ms per step, {tnames} at nside={nside} lmax={lmax}"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        tot_ms = []
-        cores, sample = None, None
+        cpu = CpuPort(nside, lmax, transforms)
+        stride = cpu.stride_for(args.ref_budget / max(1, args.steps + args.warmup))
+        vals, leg_ms, ring_ms = [], 0.0, 0.0
         for i in range(args.warmup + args.steps):
-            ms, cores, sample, _ = cpu_port_step_ms(nside, lmax, args.cpu_budget)
+            ms, leg_ms, ring_ms = cpu.step_ms(stride)
             if i >= args.warmup:
-                tot_ms.append(ms)
-        v = float(np.mean(tot_ms))
+                vals.append(ms)
+        v = float(np.mean(vals))
         emit({
-            "impl": "reference", "metric": METRIC, "value": v, "unit": "ms", "n_gpus": args.gpus,
+            "impl": "reference", "metric": metric, "value": v, "unit": "ms", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "ms", "cores": cpu.threads, "kind": "port", "extrapolated": stride > 1,
+                             "sample_stride": stride, "sample": cpu.describe(stride, leg_ms, ring_ms)},
             "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "FP64 OpenMP CPU port of the same staged algorithm (not ducc; the reference itself "
-                    "needs Julia+MPI+Ducc0 which are absent), bounded sample extrapolated to the full step"})
+            "note": "FP64 OpenMP CPU port of the same staged algorithm (NOT ducc: the reference itself needs "
+                    "Julia+MPI+Ducc0, absent from this image; bench/reference_cpu.jl times the real one where "
+                    "Julia exists).  Expect ducc's hand-vectorised kernels to be faster than this port."})
         return
 
     import torch
@@ -251,8 +298,9 @@ def main():
     else:
         comm = H.COMM_SELF
 
+    ncomps = sorted(set(c for c, _ in transforms))
     t_setup = time.perf_counter()
-    plan = H.Plan(nside, lmax, comm, 2, local_rank)
+    plan = H.Plan(nside, lmax, comm, max(ncomps), local_rank)
     mval, _ = plan.alm_info()
     minfo = plan.map_info()
     log(f"[rank {rank}] plan: nm_loc={plan.nm_loc} nalm_loc={plan.nalm_loc} nring_loc={plan.nring_loc} "
@@ -263,10 +311,9 @@ def main():
         t = torch.from_numpy(np.ascontiguousarray(a))
         return t.pin_memory()
 
-    h_alm = {1: pinned(synth_alm_shard(4096 * 4 + 0, 1, lmax, mval).view(np.float64)),
-             2: pinned(synth_alm_shard(4096 * 4 + 1, 2, lmax, mval).view(np.float64))}
-    h_map = {1: pinned(synth_map_shard(4096 * 4 + 2, 1, minfo["rings"], minfo["nphi"])),
-             2: pinned(synth_map_shard(4096 * 4 + 3, 2, minfo["rings"], minfo["nphi"]))}
+    seed0 = 4096 * args.config
+    h_alm = {c: pinned(synth_alm_shard(seed0 + c - 1, c, lmax, mval).view(np.float64)) for c in ncomps}
+    h_map = {c: pinned(synth_map_shard(seed0 + c + 1, c, minfo["rings"], minfo["nphi"])) for c in ncomps}
     d_alm = {k: v.cuda() for k, v in h_alm.items()}
     d_map = {k: v.cuda() for k, v in h_map.items()}
     d_alm_out = {k: torch.empty_like(v) for k, v in d_alm.items()}
@@ -277,26 +324,25 @@ def main():
 
     stage_acc = {}
 
+    def run_one(ncomp, d, resident):
+        if d == "a2m":
+            plan.alm2map(d_alm[ncomp] if resident else h_alm[ncomp],
+                         d_map_out[ncomp] if resident else h_map_out[ncomp], ncomp)
+        else:
+            plan.adjoint_alm2map(d_map[ncomp] if resident else h_map[ncomp],
+                                 d_alm_out[ncomp] if resident else h_alm_out[ncomp], ncomp)
+        t = plan.timings()
+        for k, v in t.items():
+            stage_acc[(ncomp, d, k)] = stage_acc.get((ncomp, d, k), 0.0) + v
+        return t["total"], plan.launches()
+
     def one_step(resident: bool):
-        """4 transforms; returns (device ms summed from the plan's CUDA events, kernel launches)."""
+        """all transforms of the config; returns (device ms summed from the plan's CUDA events, kernel launches)"""
         ms, launches = 0.0, 0
-        for ncomp in (1, 2):
-            a_in = d_alm[ncomp] if resident else h_alm[ncomp]
-            m_out = d_map_out[ncomp] if resident else h_map_out[ncomp]
-            plan.alm2map(a_in, m_out, ncomp)
-            t = plan.timings()
-            ms += t["total"]
-            launches += plan.launches()
-            for k, v in t.items():
-                stage_acc[(ncomp, "a2m", k)] = stage_acc.get((ncomp, "a2m", k), 0.0) + v
-            m_in = d_map[ncomp] if resident else h_map[ncomp]
-            a_out = d_alm_out[ncomp] if resident else h_alm_out[ncomp]
-            plan.adjoint_alm2map(m_in, a_out, ncomp)
-            t = plan.timings()
-            ms += t["total"]
-            launches += plan.launches()
-            for k, v in t.items():
-                stage_acc[(ncomp, "adj", k)] = stage_acc.get((ncomp, "adj", k), 0.0) + v
+        for ncomp, d in transforms:
+            a, b = run_one(ncomp, d, resident)
+            ms += a
+            launches += b
         return ms, launches
 
     def barrier():
@@ -324,77 +370,178 @@ def main():
             dev_ms, wall_ms = float(t[0]), float(t[1])
         return dev_ms / steps, wall_ms / steps, launches
 
+    def stage_table(steps):
+        return {f"spin{0 if c == 1 else 2}_{d}_{k}_ms": v / steps for (c, d, k), v in stage_acc.items() if k != "_"}
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_step, wall_step, launches = timed(True, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    stages = {f"spin{0 if c == 1 else 2}_{d}_{k}_ms": v / args.steps for (c, d, k), v in stage_acc.items()
-              if k != "_"}
+    stages = stage_table(args.steps)
 
     e2e = None
     if not args.no_e2e:
         e_ms, e_wall, _ = timed(False, max(1, min(args.steps, 2)), 1)
-        h2d = sum(h_alm[c].numel() * 8 + h_map[c].numel() * 8 for c in (1, 2))
-        e2e = {"value": e_wall, "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h2d),
+        h2d = sum((h_alm[c].numel() if d == "a2m" else h_map[c].numel()) * 8 for c, d in transforms)
+        d2h = sum((h_map[c].numel() if d == "a2m" else h_alm[c].numel()) * 8 for c, d in transforms)
+        e2e = {"value": e_wall, "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "device_ms": e_ms, "api": "Plan.alm2map / Plan.adjoint_alm2map (hpsht_alm2map C-ABI) on pinned "
                                          "host shards, per-rank bytes"}
 
+    # ---- stage pass: the same transforms with the stages back to back (no block overlap), for the per-stage
+    #      rooflines.  At N = 1 the timed region already runs that way. ----
+    stages_seq = stages
+    if world > 1:
+        plan.set_dev_blocks(False)
+        timed(True, 2, 1)
+        stages_seq = stage_table(2)
+        plan.set_dev_blocks(True)
+
     # ---- roofline of the dominant kernel = the Legendre kernel with the largest share of the step ----
-    steps2_c, steps2_d = plan.legendre_steps(2)
-    steps0_c, _ = plan.legendre_steps(0)
-    import ctypes as C
     tf, secs = C.c_double(), C.c_double()
     H._lib.check(H._lib.lib().hpsht_measure_fp64_peak(C.byref(tf), C.byref(secs)))
-    # 26 flop (spin 2) / 6 flop (spin 0) per (l, m, ring-pair) step, culled count
-    kernels = {
-        "k_leg2alm_s2_w (spin-2 Legendre recurrence, adjoint)": (26.0 * steps2_c, stages.get("spin2_adj_legendre_kernel_ms")),
-        "k_alm2leg_s2 (spin-2 Legendre recurrence, synthesis)": (26.0 * steps2_c, stages.get("spin2_a2m_legendre_kernel_ms")),
-        "k_leg2alm_s0_w (spin-0 Legendre recurrence, adjoint)": (6.0 * steps0_c, stages.get("spin0_adj_legendre_kernel_ms")),
-        "k_alm2leg_s0 (spin-0 Legendre recurrence, synthesis)": (6.0 * steps0_c, stages.get("spin0_a2m_legendre_kernel_ms")),
-    }
+    steps_c = {c: plan.legendre_steps(0 if c == 1 else 2)[0] for c in ncomps}
+    kname = {(1, "a2m"): "k_alm2leg_s0", (1, "adj"): "k_leg2alm_s0", (2, "a2m"): "k_alm2leg_s2", (2, "adj"): "k_leg2alm_s2"}
+    # 26 flop (spin 2) / 6 flop (spin 0) per (l, m, ring-pair) step, culled count, this rank
+    kernels = {kname[(c, d)]: ((26.0 if c == 2 else 6.0) * steps_c[c],
+                               stages_seq.get(f"spin{0 if c == 1 else 2}_{d}_legendre_kernel_ms")) for c, d in transforms}
     dom = max(kernels, key=lambda k: kernels[k][1] or 0.0)
     flop, kern_ms = kernels[dom]
     achieved = _tf(flop, kern_ms)
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same size, P = 1)
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        ent = tj.get(dom.split(" ")[0])
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        ent = tj.get(dom)
         if ent and ent.get("nside") == nside and ent.get("lmax") == lmax and world == 1:
             traffic = ent["dram_bytes_per_launch"]
+            traffic_src = ent.get("source")
     except Exception:
         pass
-    roofline = {"bound": "fp64_fma", "kernel": dom,
+    roofline = {"bound": "fp64_fma", "kernel": dom + " (+ its polar / equatorial difference-form launches)",
                 "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
-                "frac": (achieved / tf.value) if achieved else None, "traffic": traffic,
+                "frac": (achieved / tf.value) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                 "share_of_step": (kern_ms / ms_step) if kern_ms else None,
                 "peak_source": "in-repo DFMA micro-benchmark hpsht_measure_fp64_peak, same run (MEASURED_PEAKS.json "
                                "has no FP64 entry; nominal 37.2 TF at 1965 MHz)",
                 "algorithmic_flop_per_launch": flop, "kernel_ms": kern_ms,
-                "other_kernels": {k.split(" ")[0]: {"tflops": _tf(*v), "frac": (_tf(*v) / tf.value) if _tf(*v) else None,
-                                                    "kernel_ms": v[1]}
-                                  for k, v in kernels.items() if k != dom}}
+                "other_kernels": {k: {"tflops": _tf(*v), "frac": (_tf(*v) / tf.value) if _tf(*v) else None,
+                                      "kernel_ms": v[1]} for k, v in kernels.items() if k != dom}}
+
+    # ---- ring FFT against HBM, leg exchange against NVLink ----
+    hbm = 6457.1
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    fft_lines = {}
+    for c, d in transforms:
+        ms = stages_seq.get(f"spin{0 if c == 1 else 2}_{d}_ringfft_ms")
+        by = c * (16.0 * (lmax + 1) * plan.nring_loc + 8.0 * plan.npix_loc)  # SURVEY 8d, this rank
+        if ms:
+            fft_lines[f"spin{0 if c == 1 else 2}_{d}"] = {"ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6,
+                                                          "frac": by / ms / 1e6 / hbm}
+    worst = min(fft_lines, key=lambda k: fft_lines[k]["frac"]) if fft_lines else None
+    roofline_fft = None
+    if worst:
+        roofline_fft = {"bound": "hbm", "kernel": "k_leg2map / k_map2leg (ring FFT stage, " + worst + ")",
+                        "achieved": fft_lines[worst]["gbs"], "peak": hbm, "unit": "GB/s", "frac": fft_lines[worst]["frac"],
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)", "per_transform": fft_lines}
+    roofline_nvlink = None
+    if world > 1:
+        nrt = 4 * nside - 1
+        x_lines = {}
+        for c, d in transforms:
+            ms = stages_seq.get(f"spin{0 if c == 1 else 2}_{d}_exchange_ms")
+            by = c * 16.0 * plan.nm_loc * (nrt - plan.nring_loc)  # egress of this rank, SURVEY 8d
+            if ms:
+                x_lines[f"spin{0 if c == 1 else 2}_{d}"] = {"ms": ms, "egress_bytes": by, "gbs": by / ms / 1e6,
+                                                            "frac": by / ms / 1e6 / NVLINK_GBS}
+        if x_lines:
+            w = min(x_lines, key=lambda k: x_lines[k]["frac"])
+            roofline_nvlink = {"bound": "nvlink", "kernel": "grouped ncclSend/ncclRecv + k_pack / k_unpack (" + w + ")",
+                               "achieved": x_lines[w]["gbs"], "peak": NVLINK_GBS, "unit": "GB/s", "frac": x_lines[w]["frac"],
+                               "peak_source": "NVLink 5 nominal, per direction per GPU", "per_transform": x_lines,
+                               "note": "measured with the stages back to back (HPSHT_DEV_BLOCKS off); in the timed "
+                                       "region the exchange of a ring block runs behind the next block's Legendre kernels"}
+
+    # ---- parity (after the timed region; the oracle is the checker only) ----
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(plan, H, torch, dist, world, rank, nside, lmax, ncomps, seed0, mval, minfo,
+                              d_alm, d_map, d_alm_out, d_map_out)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, cores, sample, extra = cpu_port_step_ms(nside, lmax, args.cpu_budget)
-            cpu_baseline = {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": sample}
+            cpu = CpuPort(nside, lmax, transforms)
+            stride = cpu.stride_for(args.cpu_budget)
+            v, leg_ms, ring_ms = cpu.step_ms(stride)
+            cpu_baseline = {"value": v, "unit": "ms", "cores": cpu.threads, "kind": "port", "extrapolated": stride > 1,
+                            "sample_stride": stride, "sample": cpu.describe(stride, leg_ms, ring_ms)}
         except Exception as e:  # pragma: no cover
             log("cpu baseline failed:", e)
 
     if rank == 0:
-        out = {"metric": METRIC, "value": ms_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
+        out = {"metric": metric, "value": ms_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_step, "wall_ms_per_step": wall_step,
                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
-               "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline, "stages_ms": stages,
-               "fp64_peak_tflops_measured": tf.value}
+               "e2e": e2e, "roofline": roofline, "roofline_fft": roofline_fft, "roofline_nvlink": roofline_nvlink,
+               "parity": parity, "cpu_baseline": cpu_baseline, "stages_ms": stages,
+               "stages_back_to_back_ms": stages_seq if world > 1 else None, "fp64_peak_tflops_measured": tf.value}
         emit(out)
     plan.destroy()
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_block(plan, H, torch, dist, world, rank, nside, lmax, ncomps, seed0, mval, minfo, d_alm, d_map,
+                 d_alm_out, d_map_out):
+    """(1) adjointness <f, Y a> = <Y^T f, a>_w (localdot weights, src/alm.jl:634-644) with both sides summed over
+    all ranks; (2) a sample of rank 0's rings of Y a against the long-double oracle on the regenerated full alm."""
+    out = {"tolerance": 1e-12, "adjointness": {}, "rings_vs_oracle": {}}
+    w = torch.from_numpy(np.concatenate([np.full(lmax + 1 - int(m), 1.0 if m == 0 else 2.0) for m in mval])).cuda()
+    ok = True
+    for c in ncomps:
+        spin = 0 if c == 1 else 2
+        plan.alm2map(d_alm[c], d_map_out[c], c)
+        plan.adjoint_alm2map(d_map[c], d_alm_out[c], c)
+        a = d_alm[c].view(c, -1, 2)
+        o = d_alm_out[c].view(c, -1, 2)
+        v = torch.stack([(d_map[c] * d_map_out[c]).sum(), (w[None, :, None] * o * a).sum(),
+                         (d_map[c] ** 2).sum(), (d_map_out[c] ** 2).sum()])
+        if world > 1:
+            dist.all_reduce(v)
+        lhs, rhs, n1, n2 = (float(x) for x in v)
+        res = abs(lhs - rhs) / np.sqrt(n1 * n2)
+        out["adjointness"][f"spin{spin}"] = res
+        ok = ok and res <= 1e-12
+        if rank == 0:
+            try:
+                from oracle import parity as PR
+
+                sel = PR.sample_rings(nside, minfo["rings"], n_bulk=4)
+                sel = sel[np.linspace(0, len(sel) - 1, min(len(sel), 10)).astype(int)]
+                loc = {int(r): (int(s), int(n)) for r, s, n in zip(minfo["rings"], minfo["rstart0"], minfo["nphi"])}
+                mp = d_map_out[c]
+                got = {int(r): mp[:, loc[int(r)][0]:loc[int(r)][0] + loc[int(r)][1]].cpu().numpy() for r in sel}
+                alm_full = synth_alm_shard(seed0 + c - 1, c, lmax, np.arange(lmax + 1))
+                res = PR.synthesis_parity(nside, lmax, spin, alm_full, got, sel)
+                out["rings_vs_oracle"][f"spin{spin}"] = {k: res[k] for k in ("rel_l2", "max_ring", "max_polar_ring",
+                                                                             "n_rings", "n_pixels")}
+                ok = ok and res["rel_l2"] <= 1e-12
+            except Exception as e:  # pragma: no cover
+                out["rings_vs_oracle"][f"spin{spin}"] = {"error": str(e)}
+                ok = False
+    out["rel_l2"] = max([v["rel_l2"] for v in out["rings_vs_oracle"].values() if "rel_l2" in v and v["rel_l2"]] or [None]) \
+        if out["rings_vs_oracle"] else None
+    out["ok"] = bool(ok)
+    out["what"] = ("adjointness: |<f,Ya> - <Y^T f,a>_w| / (|f| |Ya|), all ranks; rings_vs_oracle: relative L2 of rank 0's "
+                   "sampled rings of Y a against oracle/sht_oracle.c (long double; reference ring cut and pair "
+                   "colatitude applied, oracle/parity.py)")
+    return out
 
 
 def _tf(flop, ms):

@@ -58,6 +58,7 @@ SIGNATURES = {
     "hpsht_alm2map_async": (C.c_int, [vp, vp, vp, C.c_int, vp]),
     "hpsht_adjoint_alm2map_async": (C.c_int, [vp, vp, vp, C.c_int, vp]),
     "hpsht_plan_synchronize": (C.c_int, [vp]),
+    "hpsht_plan_set_dev_blocks": (C.c_int, [vp, C.c_int]),
     "hpsht_plan_scatter_alm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
     "hpsht_plan_gather_alm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
     "hpsht_plan_scatter_map": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),

@@ -1075,6 +1075,12 @@ int hpsht_adjoint_alm2map_async(hpsht_plan* plan, const double* d_map, double* d
     plan->run(false, d_map, d_alm, ncomp, true, static_cast<cudaStream_t>(cuda_stream));
   });
 }
+int hpsht_plan_set_dev_blocks(hpsht_plan* plan, int on) {
+  return guarded([&] {
+    HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
+    plan->dev_blocks = on != 0;
+  });
+}
 int hpsht_plan_synchronize(hpsht_plan* plan) {
   return guarded([&] {
     HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");

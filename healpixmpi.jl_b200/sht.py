@@ -125,6 +125,23 @@ class Plan:
     def adjoint_alm2map(self, mp, alm, ncomp: int, nthreads: int = 0) -> None:
         _lib.check(_lib.lib().hpsht_adjoint_alm2map(self.handle, _lib.ptr(mp), _lib.ptr(alm), ncomp, nthreads))
 
+    def alm2map_async(self, d_alm, d_map, ncomp: int, cuda_stream: int = 0) -> None:
+        """Stream-ordered alm2map! on device-resident shards: ordered after the work queued on ``cuda_stream``
+        (a raw cudaStream_t, e.g. ``torch.cuda.current_stream().cuda_stream``); does not block the host."""
+        _lib.check(_lib.lib().hpsht_alm2map_async(self.handle, _lib.ptr(d_alm), _lib.ptr(d_map), ncomp,
+                                                  C.c_void_p(cuda_stream)))
+
+    def adjoint_alm2map_async(self, d_map, d_alm, ncomp: int, cuda_stream: int = 0) -> None:
+        _lib.check(_lib.lib().hpsht_adjoint_alm2map_async(self.handle, _lib.ptr(d_map), _lib.ptr(d_alm), ncomp,
+                                                          C.c_void_p(cuda_stream)))
+
+    def synchronize(self) -> None:
+        _lib.check(_lib.lib().hpsht_plan_synchronize(self.handle))
+
+    def set_dev_blocks(self, on: bool) -> None:
+        """P > 1: ring-block pipelining of device-pointer calls (same value on every rank)."""
+        _lib.check(_lib.lib().hpsht_plan_set_dev_blocks(self.handle, 1 if on else 0))
+
     # ---- shards on the device (SURVEY 8f N1-N3): numpy arrays or torch CUDA tensors alike ----
     def scatter_alm(self, global_alm, alm, ncomp: int, root: int = 0) -> None:
         """MPI.Scatter!(alm, d_alm; root) (src/alm.jl:219-307): ``global_alm`` [ncomp][nalm_tot] complex is read

@@ -159,6 +159,11 @@ int hpsht_alm2map_async(hpsht_plan* plan, const double* d_alm, double* d_map, in
 int hpsht_adjoint_alm2map_async(hpsht_plan* plan, const double* d_map, double* d_alm, int ncomp,
                                 void* cuda_stream);
 int hpsht_plan_synchronize(hpsht_plan* plan);
+/* P > 1: run device-pointer calls ring block by ring block, the leg exchange / ring FFT of a block behind the
+   Legendre kernels of the next one (default on; HPSHT_DEV_BLOCKS=0 in the environment turns it off at plan
+   creation).  Off = the stages run back to back, which is what the per-stage timers want.  Must be set
+   identically on every rank of the plan.                                                 */
+int hpsht_plan_set_dev_blocks(hpsht_plan* plan, int on);
 
 /* ---- shards on the device: scatter / gather / algebra -------------------
    All collective over the plan's ranks; host or device pointers.  `ncomp` components are moved

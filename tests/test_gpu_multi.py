@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("host_blocks", ["1", "3"])
-@pytest.mark.parametrize("nranks", [2, 4, 8])
+@pytest.mark.parametrize("nranks", [2, 3, 4, 6, 8])
 def test_nccl_ranks_match_single_rank_and_oracle(nranks, host_blocks):
     """host_blocks 1: one exchange per transform; 3: ring blocks pipelined (Legendre | exchange | ring FFT |
     host copy), which the host-array API uses at large sizes."""
