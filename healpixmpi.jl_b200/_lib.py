@@ -10,7 +10,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhpsht_b200.so")
+# HPSHT_B200_LIB: another build of the same library (kernel experiments, tools/build_variant.sh)
+LIB_PATH = os.environ.get("HPSHT_B200_LIB") or os.path.join(_HERE, "libhpsht_b200.so")
 
 i64 = C.c_int64
 i64p = C.POINTER(C.c_int64)

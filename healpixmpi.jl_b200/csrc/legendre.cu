@@ -626,26 +626,39 @@ __global__ void __launch_bounds__((NW + 1) * 32) k_alm2leg_s2(LegParams P) {
 // ================================================================================================
 namespace {
 
-// sum over the 32 lanes of v[k], k < 16, through shared memory; every lane returns the total of value
-// (lane & 15)
-__device__ __forceinline__ double warp_reduce16_smem(const double (&v)[16], double (*tr)[33], int lane) {
-  __syncwarp();  // readers of the previous round are done
+// The 32-lane reduction of 16 per-lane partial sums goes through a padded shared-memory transpose, split in
+// two so that the second half overlaps the next group's FMAs: tr_store parks the 16 values, tr_reduce (one
+// group later, other buffer in between) lets every lane add up one value's 16-lane half and combines the halves
+// with one shuffle -- every lane returns the total of value (lane & 15).
+__device__ __forceinline__ void tr_store(const double (&v)[16], double (*tr)[33], int lane) {
 #pragma unroll
   for (int k = 0; k < 16; ++k) tr[k][lane] = v[k];
   __syncwarp();
-  const int j = lane & 15, h = (lane >> 4) * 16;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-  for (int t = 0; t < 16; t += 4) {
-    s0 += tr[j][h + t];
-    s1 += tr[j][h + t + 1];
-    s2 += tr[j][h + t + 2];
-    s3 += tr[j][h + t + 3];
-  }
-  double s = (s0 + s1) + (s2 + s3);
+}
+// quarter t4 (0..3) of a lane's 16 entries; called once per recurrence step so that the loads and adds spread
+// over the step's FMAs
+struct TrSum {
+  double s0, s1, s2, s3;
+};
+__device__ __forceinline__ void tr_quarter(TrSum& a, const double (*tr)[33], int lane, int t4) {
+  const int j = lane & 15, h = (lane >> 4) * 16 + 4 * t4;
+  a.s0 += tr[j][h];
+  a.s1 += tr[j][h + 1];
+  a.s2 += tr[j][h + 2];
+  a.s3 += tr[j][h + 3];
+}
+__device__ __forceinline__ double tr_finish(const TrSum& a) {
+  double s = (a.s0 + a.s1) + (a.s2 + a.s3);
   s += __shfl_xor_sync(0xffffffffu, s, 16);
   return s;
 }
+__device__ __forceinline__ double tr_reduce(const double (*tr)[33], int lane) {
+  TrSum a = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) tr_quarter(a, tr, lane, t);
+  return tr_finish(a);
+}
+constexpr int RES_DUMMY = LEG_CHUNK / 4;  // s_res slot (of 16 doubles) that takes the reduction of "nothing pending"
 
 // the tiles of an adjoint item: segment A = [p0, split) in the item's class, segment B = [split, pend) in X
 struct TileWalk {
@@ -669,8 +682,8 @@ template <int R, int MODE>
 __global__ void __launch_bounds__(32, (R <= 4) ? 16 : 1) k_leg2alm_s0(LegParams P) {
   constexpr bool DIFF = MODE != 0, ALT = MODE == 2;
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
-  __shared__ double s_tr[16][33];
-  __shared__ double s_res[LEG_CHUNK * 4];  // reduced sums of the current chunk
+  __shared__ double s_tr[2][16][33];
+  __shared__ double s_res[LEG_CHUNK * 4 + 16];  // reduced sums of the current chunk (+ the dummy slot)
   __shared__ __align__(8) uint64_t s_full[NSTAGE];
   constexpr int TILE = R * 32;
 
@@ -705,6 +718,7 @@ __global__ void __launch_bounds__(32, (R <= 4) ? 16 : 1) k_leg2alm_s0(LegParams 
   const double k0 = P.k0[mi];
   double* gpart = P.part + (size_t)P.partoff[blockIdx.x] * 4;
   int cg = 0;
+  int tb = 0;  // s_tr buffer the next group parks its sums in
 
   for (int tile = 0; tile < tw.ntile; ++tile) {
     const bool inA = tile < tw.ntA;
@@ -770,6 +784,7 @@ __global__ void __launch_bounds__(32, (R <= 4) ? 16 : 1) k_leg2alm_s0(LegParams 
       for (int k = 0; k < 8; ++k) s_res[k * 32 + lane] = 0.0;  // groups that only ramp contribute 0
       mbar_wait(&s_full[st], (cg / NSTAGE) & 1);
       const int ng = min(LEG_CHUNK, nsteps - c * LEG_CHUNK) / LEG_GROUP;
+      int pend = RES_DUMMY;  // 4-step group whose 16 partial sums are parked in s_tr[tb ^ 1]
       if (warp_act) {
 #pragma unroll 1
         for (int g = 0; g < ng; ++g) {
@@ -777,25 +792,35 @@ __global__ void __launch_bounds__(32, (R <= 4) ? 16 : 1) k_leg2alm_s0(LegParams 
           if (w_any0) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              double acc[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+              // the previous 4-step group's reduction runs next to this group's FMAs, a quarter per step
+              TrSum ts = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
               for (int s = 0; s < 4; ++s) {
                 const Coef ab = cf[h * 4 + s];
+                tr_quarter(ts, s_tr[tb ^ 1], lane, s);
+                // the step's four sums over this thread's R rings go straight to the transpose buffer
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                   const double pv = (ALT && (s & 1)) ? -u[r] : u[r];
-                  acc[4 * s + 0] = fma(pv, er[r], acc[4 * s + 0]);
-                  acc[4 * s + 1] = fma(pv, ei[r], acc[4 * s + 1]);
-                  acc[4 * s + 2] = fma(pv, orr[r], acc[4 * s + 2]);
-                  acc[4 * s + 3] = fma(pv, oi[r], acc[4 * s + 3]);
+                  a0 = fma(pv, er[r], a0);
+                  a1 = fma(pv, ei[r], a1);
+                  a2 = fma(pv, orr[r], a2);
+                  a3 = fma(pv, oi[r], a3);
                   rec_step<DIFF>(fma(ab.a, y[r], ab.b), u[r], v[r]);
                 }
+                s_tr[tb][4 * s + 0][lane] = a0;
+                s_tr[tb][4 * s + 1][lane] = a1;
+                s_tr[tb][4 * s + 2][lane] = a2;
+                s_tr[tb][4 * s + 3][lane] = a3;
               }
-              const double tot = warp_reduce16_smem(acc, s_tr, lane);
-              // 4-step group q = 2g + h: lower half-warp keeps even q, upper half odd q
-              if (lane < 16) s_res[(g * 2 + h) * 16 + lane] = tot;
+              {
+                const double tot = tr_finish(ts);
+                if (lane < 16) s_res[pend * 16 + lane] = tot;
+              }
+              __syncwarp();
+              pend = g * 2 + h;  // 4-step group q = 2g + h
+              tb ^= 1;
             }
           } else {
 #pragma unroll
@@ -819,6 +844,10 @@ __global__ void __launch_bounds__(32, (R <= 4) ? 16 : 1) k_leg2alm_s0(LegParams 
           }
         }
       }
+      {  // the last group's reduction
+        const double tot = tr_reduce(s_tr[tb ^ 1], lane);
+        if (lane < 16) s_res[pend * 16 + lane] = tot;
+      }
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 8; ++k) gp[k * 32] = old[k] + s_res[k * 32 + lane];
@@ -830,7 +859,7 @@ __global__ void __launch_bounds__(32, (R <= 4) ? 16 : 1) k_leg2alm_s0(LegParams 
 // spin 2 adjoint:  G+ = sum_pairs d+ w+N + (-1)^(l+m) d- w+S ,  G- = sum_pairs d- w-N + (-1)^(l+m) d+ w-S
 // with w+- = Q +- iU of the ring
 template <int R, int MODE>
-__global__ void __launch_bounds__(32, (R <= 2) ? 16 : (R <= 3 ? 12 : (R <= 4 ? 10 : 1))) k_leg2alm_s2(LegParams P) {
+__global__ void __launch_bounds__(32, (R <= 4) ? 10 : 1) k_leg2alm_s2(LegParams P) {
   constexpr bool DIFF = MODE != 0;
   __shared__ Coef s_coef[NSTAGE][LEG_CHUNK];
   __shared__ __align__(16) double s_ca[NSTAGE][LEG_CHUNK];
@@ -967,6 +996,8 @@ __global__ void __launch_bounds__(32, (R <= 2) ? 16 : (R <= 3 ? 12 : (R <= 4 ? 1
           const Coef* cf = &s_coef[st][g * LEG_GROUP];
           const double2* ca = reinterpret_cast<const double2*>(&s_ca[st][g * LEG_GROUP]);
           if (w_any0) {
+            // (the pipelined / per-step forms of the spin-0 kernel measured 1 - 3 % slower here: the 13 doubles of
+            // state per ring leave the scheduler no room, profiles/r02_adjoint_experiments.md)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               double acc[16];
@@ -993,7 +1024,9 @@ __global__ void __launch_bounds__(32, (R <= 2) ? 16 : (R <= 3 ? 12 : (R <= 4 ? 1
                   rec_step<DIFF>(fma(a, y[r], cc.b), um[r], vm[r]);
                 }
               }
-              const double tot = warp_reduce16_smem(acc, s_tr, lane);
+              __syncwarp();  // readers of the previous round are done
+              tr_store(acc, s_tr, lane);
+              const double tot = tr_reduce(s_tr, lane);
               if (lane < 16) s_res[(g * 2 + h) * 16 + lane] = tot;
             }
           } else {
@@ -1328,7 +1361,8 @@ void LegendreStage::setup(int64_t lmax, const int64_t* mval, const int64_t* msta
   if (!ev_fork_) HP_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   if (!ev_join_) HP_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
   if (!side_) HP_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
-  blk_pair_[0] = {0, (int)np};
+  blk_pair_[0].assign(2, 0);
+  blk_pair_[0][1] = (int)np;
   blk_pair_[1].clear();
   have_[0] = have_[1] = false;
 }
