@@ -60,6 +60,7 @@ SIGNATURES = {
     "hpsht_adjoint_alm2map_async": (C.c_int, [vp, vp, vp, C.c_int, vp]),
     "hpsht_plan_synchronize": (C.c_int, [vp]),
     "hpsht_plan_set_dev_blocks": (C.c_int, [vp, C.c_int]),
+    "hpsht_ring_block_ranges": (C.c_int, [i64, i64, C.c_int, C.POINTER(C.c_int), vp, vp, C.c_int]),
     "hpsht_plan_scatter_alm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
     "hpsht_plan_gather_alm": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
     "hpsht_plan_scatter_map": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),

@@ -272,13 +272,51 @@ void hpsht_plan::ensure_stages() {
 // ring pairs cut into HB tile-aligned blocks the copy / exchange / FFT of one block overlaps the Legendre
 // work of the others (HPSHT_HOST_BLOCKS, 1 = off).  The blocks are ranges of the global pole -> equator
 // pair list; with round-robin ring ownership every rank's share of a block is a contiguous range
-// [blo, bhi) of its local rings.  Everything that decides HB is the same on every rank (the ranks of a
-// collective call must cut the same blocks): nside, P and the environment.
-void hpsht_plan::setup_blocks() {
-  HB = 1;
+// [blo, bhi) of its local rings.  Everything that decides the cut is the same on every rank (the ranks of a
+// collective call must cut the same blocks): nside, lmax, P and the environment -- no rank-local quantity.
+namespace {
+int wanted_ring_blocks(int64_t nside, int P) {
   const char* eb = getenv("HPSHT_HOST_BLOCKS");
   int want = eb ? std::max(1, atoi(eb)) : (P <= 2 ? 6 : 4);
   if (!eb && 12 * nside * nside / P < (1 << 22)) want = 1;  // small maps: the copies are microseconds
+  return want;
+}
+// [block][rank] local ring ranges of the cut `bp` (first pair of each block + end); false: exotic ring order
+bool ring_block_ranges(const std::vector<PairHost>& pairs, const std::vector<int>& bp, const std::vector<int64_t>& nr_of,
+                       std::vector<int64_t>& bj_lo, std::vector<int64_t>& bj_hi) {
+  const int P = (int)nr_of.size(), HB = (int)bp.size() - 1;
+  std::vector<int64_t> roff((size_t)P + 1, 0);  // first slot of every rank in thetatot order
+  for (int t = 0; t < P; ++t) roff[(size_t)t + 1] = roff[(size_t)t] + nr_of[(size_t)t];
+  bj_lo.assign((size_t)HB * P, 0);
+  bj_hi.assign((size_t)HB * P, 0);
+  for (int b = 0; b < HB; ++b) {
+    std::vector<int64_t> lo((size_t)P, INT64_MAX), hi((size_t)P, -1), cnt((size_t)P, 0);
+    for (int p = bp[(size_t)b]; p < bp[(size_t)b + 1]; ++p)
+      for (int64_t slot : {pairs[(size_t)p].slotN, pairs[(size_t)p].slotS}) {
+        if (slot < 0) continue;
+        const int t = (int)(std::upper_bound(roff.begin(), roff.end(), slot) - roff.begin()) - 1;
+        const int64_t j = slot - roff[(size_t)t];
+        lo[(size_t)t] = std::min(lo[(size_t)t], j);
+        hi[(size_t)t] = std::max(hi[(size_t)t], j + 1);
+        ++cnt[(size_t)t];
+      }
+    for (int t = 0; t < P; ++t) {
+      const int64_t prev = b == 0 ? nr_of[(size_t)t] : bj_lo[(size_t)(b - 1) * P + t];
+      if (cnt[(size_t)t] == 0) lo[(size_t)t] = hi[(size_t)t] = prev;  // no ring of this rank in the block
+      // blocks run pole -> equator = towards lower local ring indices, without gaps
+      if (cnt[(size_t)t] != hi[(size_t)t] - lo[(size_t)t] || hi[(size_t)t] != prev) return false;
+      bj_lo[(size_t)b * P + t] = lo[(size_t)t];
+      bj_hi[(size_t)b * P + t] = hi[(size_t)t];
+    }
+  }
+  for (int t = 0; t < P; ++t)
+    if (bj_lo[(size_t)(HB - 1) * P + t] != 0) return false;
+  return true;
+}
+}  // namespace
+
+void hpsht_plan::setup_blocks() {
+  HB = 1;
   const char* ed = getenv("HPSHT_DEV_BLOCKS");
   dev_blocks = ed ? atoi(ed) != 0 : true;
   std::vector<double> w((size_t)nr_tot);
@@ -286,36 +324,13 @@ void hpsht_plan::setup_blocks() {
     std::vector<int64_t> tot = rr_rindexes_tot(2 * nside, P);
     for (size_t i = 0; i < tot.size(); ++i) w[i] = (double)healpix_ring(nside, tot[i]).nphi;
   }
-  HB = leg.setup_blocks(want, w.data());
+  HB = leg.setup_blocks(wanted_ring_blocks(nside, P), w.data());
   if (HB <= 1) return;
-  std::vector<int64_t> roff((size_t)P + 1, 0);  // first slot of every rank in thetatot order
-  for (int t = 0; t < P; ++t) roff[(size_t)t + 1] = roff[(size_t)t] + nr_of[(size_t)t];
-  bj_lo.assign((size_t)HB * P, 0);
-  bj_hi.assign((size_t)HB * P, 0);
-  bool ok = true;
-  for (int b = 0; b < HB && ok; ++b) {
-    std::vector<int64_t> lo((size_t)P, INT64_MAX), hi((size_t)P, -1), cnt((size_t)P, 0);
-    for (int64_t slot : leg.block_slot_list(1, b)) {
-      const int t = (int)(std::upper_bound(roff.begin(), roff.end(), slot) - roff.begin()) - 1;
-      const int64_t j = slot - roff[(size_t)t];
-      lo[(size_t)t] = std::min(lo[(size_t)t], j);
-      hi[(size_t)t] = std::max(hi[(size_t)t], j + 1);
-      ++cnt[(size_t)t];
-    }
-    for (int t = 0; t < P; ++t) {
-      if (cnt[(size_t)t] == 0) {  // no ring of this rank in the block: empty range at the running boundary
-        lo[(size_t)t] = hi[(size_t)t] = b == 0 ? nr_of[(size_t)t] : blo(1, b - 1, t);
-      }
-      // blocks run pole -> equator = towards lower local ring indices, without gaps
-      ok = ok && cnt[(size_t)t] == hi[(size_t)t] - lo[(size_t)t] &&
-           hi[(size_t)t] == (b == 0 ? nr_of[(size_t)t] : blo(1, b - 1, t));
-      bj_lo[(size_t)b * P + t] = lo[(size_t)t];
-      bj_hi[(size_t)b * P + t] = hi[(size_t)t];
-    }
-    if (b == HB - 1)
-      for (int t = 0; t < P; ++t) ok = ok && lo[(size_t)t] == 0;
-  }
-  if (!ok) {  // exotic ring order: no blocking
+  std::vector<int> bp;
+  // the pair list the Legendre stage cut is the one build_pairs gives for thetatot
+  const std::vector<PairHost> pairs = build_pairs(lmax, nr_tot, thetatot.data());
+  bp = cut_ring_blocks(pairs, wanted_ring_blocks(nside, P), w.data());
+  if (!ring_block_ranges(pairs, bp, nr_of, bj_lo, bj_hi)) {  // exotic ring order: no blocking
     HB = leg.setup_blocks(1, w.data());
     return;
   }
@@ -1073,6 +1088,35 @@ int hpsht_adjoint_alm2map_async(hpsht_plan* plan, const double* d_map, double* d
   return guarded([&] {
     HP_REQUIRE(plan, HPSHT_ERR_ARG, "null plan");
     plan->run(false, d_map, d_alm, ncomp, true, static_cast<cudaStream_t>(cuda_stream));
+  });
+}
+int hpsht_ring_block_ranges(int64_t nside, int64_t lmax, int n_ranks, int* nblocks, int64_t* lo, int64_t* hi,
+                            int capacity) {
+  return guarded([&] {
+    HP_REQUIRE(nblocks && nside >= 1 && lmax >= 0 && n_ranks >= 1, HPSHT_ERR_ARG, "bad argument");
+    const int64_t eq = 2 * nside, nr_tot = 2 * eq - 1;
+    std::vector<int64_t> tot = rr_rindexes_tot(eq, n_ranks), nr_of((size_t)n_ranks);
+    std::vector<double> theta((size_t)nr_tot), w((size_t)nr_tot);
+    for (size_t i = 0; i < tot.size(); ++i) {
+      const RingGeom g = healpix_ring(nside, tot[i]);
+      theta[i] = g.theta;
+      w[i] = (double)g.nphi;
+    }
+    for (int t = 0; t < n_ranks; ++t) nr_of[(size_t)t] = rr_nrings(eq, t, n_ranks);
+    const std::vector<PairHost> pairs = build_pairs(lmax, nr_tot, theta.data());
+    std::vector<int> bp = cut_ring_blocks(pairs, wanted_ring_blocks(nside, n_ranks), w.data());
+    std::vector<int64_t> l, h;
+    if (bp.size() <= 2 || !ring_block_ranges(pairs, bp, nr_of, l, h)) {
+      bp = {0, (int)pairs.size()};
+      l.assign((size_t)n_ranks, 0);
+      h = nr_of;
+    }
+    *nblocks = (int)bp.size() - 1;
+    HP_REQUIRE(!lo || !hi || (int64_t)l.size() <= capacity, HPSHT_ERR_ARG, "capacity too small");
+    if (lo && hi) {
+      std::copy(l.begin(), l.end(), lo);
+      std::copy(h.begin(), h.end(), hi);
+    }
   });
 }
 int hpsht_plan_set_dev_blocks(hpsht_plan* plan, int on) {

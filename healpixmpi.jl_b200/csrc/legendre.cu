@@ -1368,10 +1368,9 @@ void LegendreStage::setup(int64_t lmax, const int64_t* mval, const int64_t* msta
 }
 
 // ---- ring blocks -----------------------------------------------------------------------------
-int LegendreStage::setup_blocks(int want, const double* slot_weight) {
-  std::vector<int>& bp = blk_pair_[1];
-  bp.clear();
-  const int np = (int)npairs_;
+std::vector<int> cut_ring_blocks(const std::vector<PairHost>& pairs, int want, const double* slot_weight) {
+  std::vector<int> bp;
+  const int np = (int)pairs.size();
   if (want < 1) want = 1;
   bp.push_back(0);
   // Preferred cut: multiples of the least common multiple of the kernels' tile sizes (512 pairs), so that
@@ -1391,8 +1390,8 @@ int LegendreStage::setup_blocks(int want, const double* slot_weight) {
     // small problems (tests): equal-weight blocks on warp-aligned boundaries
     std::vector<double> cum((size_t)np + 1, 0.0);
     for (int p = 0; p < np; ++p) {
-      double w = slot_weight[pairs_[(size_t)p].slotN];
-      if (pairs_[(size_t)p].slotS >= 0) w += slot_weight[pairs_[(size_t)p].slotS];
+      double w = slot_weight[pairs[(size_t)p].slotN];
+      if (pairs[(size_t)p].slotS >= 0) w += slot_weight[pairs[(size_t)p].slotS];
       cum[(size_t)p + 1] = cum[(size_t)p] + w;
     }
     for (int b = 1; b < want; ++b) {
@@ -1403,6 +1402,11 @@ int LegendreStage::setup_blocks(int want, const double* slot_weight) {
     }
   }
   bp.push_back(np);
+  return bp;
+}
+
+int LegendreStage::setup_blocks(int want, const double* slot_weight) {
+  blk_pair_[1] = cut_ring_blocks(pairs_, want, slot_weight);
   have_[0] = have_[1] = false;
   return nblocks(1);
 }

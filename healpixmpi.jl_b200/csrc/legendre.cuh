@@ -135,5 +135,7 @@ class LegendreStage {
 
 // Generic N/S pair detection on an arbitrary theta list (pole -> equator order).
 std::vector<PairHost> build_pairs(int64_t lmax, int64_t nring, const double* theta);
+// first pair of each ring block (+ the end): the pole -> equator pair list cut into <= want ranges (host only)
+std::vector<int> cut_ring_blocks(const std::vector<PairHost>& pairs, int want, const double* slot_weight);
 
 }  // namespace hpsht

@@ -79,44 +79,6 @@ function map2leg!(map::StridedMatrix{Float64}, leg::StridedArray{ComplexF64,3}, 
                 nthreads))
     leg
 end
-# Shards on the device (SURVEY 8f N1-N3).  Methods to add next to src/alm.jl:621-660, 693-713 and
-# src/cl.jl:33-38; `comp` arguments are 1-based columns of d_alm.alm as in the reference.
-function dot_fused(a, b; comp1::Integer = 1, comp2::Integer = 1, nside::Integer)
-    comm = (a.info.comm == b.info.comm) ? a.info.comm : throw(DomainError(0, "Communicators must match"))
-    p = plan_for(nside, a.info.lmax, comm)
-    res = Ref{Float64}(0.0)
-    check(ccall((:hpsht_plan_dot, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{Float64}),
-                p.handle, pointer(a.alm, (comp1 - 1) * size(a.alm, 1) + 1),
-                pointer(b.alm, (comp2 - 1) * size(b.alm, 1) + 1), res))
-    res[]
-end
-
-function almxfl_fused!(alm, fl::Vector{Float64}; nside::Integer)
-    p = plan_for(nside, alm.info.lmax, alm.info.comm)
-    check(ccall((:hpsht_plan_almxfl, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Float64}, Int64, Cint),
-                p.handle, alm.alm, fl, length(fl), size(alm.alm, 2)))
-    alm
-end
-
-function alm2cl_fused(a, b; comp1::Integer = 1, comp2::Integer = 1, nside::Integer)
-    p = plan_for(nside, a.info.lmax, a.info.comm)
-    cl = zeros(Float64, a.info.lmax + 1)
-    check(ccall((:hpsht_plan_alm2cl, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Float64}),
-                p.handle, pointer(a.alm, (comp1 - 1) * size(a.alm, 1) + 1),
-                pointer(b.alm, (comp2 - 1) * size(b.alm, 1) + 1), cl))
-    cl
-end
-
-# Scatter! / Gather! data movement for an already described shard (d_alm.info filled as in src/alm.jl:159-176):
-# global_alm is the root's Alm.alm (m-major), ignored elsewhere.
-function scatter_alm_fused!(global_alm::Union{Nothing,Vector{ComplexF64}}, d_alm; root::Integer = 0, nside::Integer)
-    p = plan_for(nside, d_alm.info.lmax, d_alm.info.comm)
-    g = global_alm === nothing ? Ptr{ComplexF64}(C_NULL) : pointer(global_alm)
-    check(ccall((:hpsht_plan_scatter_alm, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint, Cint),
-                p.handle, g, d_alm.alm, 1, root))
-    d_alm
-end
-
 end # module Sht
 
 # ------------------------------------------------------------------------------------------------
@@ -145,8 +107,39 @@ mutable struct Plan
     end
 end
 
-const PLANS = Dict{Tuple{Int,Int,MPI.Comm},Plan}()
-plan_for(nside, lmax, comm; kw...) = get!(() -> Plan(nside, lmax, comm; kw...), PLANS, (nside, lmax, comm))
+# The geometry a plan was built with is part of the cache key (a DMap with another thetatot / phi0 must not
+# reuse a stale plan).
+const PLANS = Dict{Tuple{Int,Int,MPI.Comm,UInt64},Plan}()
+function plan_for(nside, lmax, comm; thetatot = nothing, phi0 = nothing, kw...)
+    key = (Int(nside), Int(lmax), comm, hash((thetatot, phi0)))
+    get!(() -> Plan(nside, lmax, comm; thetatot = thetatot, phi0 = phi0, kw...), PLANS, key)
+end
+
+# The raw pointers handed to the library must describe exactly the shard the plan derives from
+# (nside, lmax, rank, nranks): compare sizes and descriptor arrays, throw DomainError otherwise
+# (src/sht.jl:76-77 style) instead of letting the device read or write out of bounds.
+function check_shards(p::Plan, d_alm, d_map)
+    s = [Ref{Int64}(0) for i in 1:5]
+    check(ccall((:hpsht_plan_sizes, lib), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Int64}),
+                p.handle, s[1], s[2], s[3], s[4], s[5]))
+    nm, nalm, nr, npix = s[1][], s[2][], s[3][], s[4][]
+    (d_alm.info.mmax == d_alm.info.lmax) || throw(DomainError(d_alm.info.mmax, "mmax must equal lmax"))
+    (size(d_alm.alm, 1) == nalm && length(d_alm.info.mval) == nm) ||
+        throw(DomainError(size(d_alm.alm, 1), "DAlm shard does not match the plan (nalm_loc = $nalm, nm_loc = $nm)"))
+    (size(d_map.pixels, 1) == npix && length(d_map.info.rings) == nr) ||
+        throw(DomainError(size(d_map.pixels, 1), "DMap shard does not match the plan (npix_loc = $npix, nring_loc = $nr)"))
+    mval = Vector{Int64}(undef, nm); mstart = Vector{Int64}(undef, nm)
+    check(ccall((:hpsht_plan_alm_info, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), p.handle, mval, mstart))
+    (mval == d_alm.info.mval && mstart .+ 1 == d_alm.info.mstart) ||
+        throw(DomainError(0, "DAlm.info.mval / mstart differ from the plan's round-robin shard"))
+    rings = Vector{Int64}(undef, nr); rstart = Vector{Int64}(undef, nr)
+    check(ccall((:hpsht_plan_map_info, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                p.handle, rings, rstart, C_NULL, C_NULL, C_NULL, C_NULL))
+    (rings == d_map.info.rings && rstart .+ 1 == d_map.info.rstart) ||
+        throw(DomainError(0, "DMap.info.rings / rstart differ from the plan's round-robin shard"))
+    nothing
+end
 
 # Methods to add in src/sht.jl in place of the allocating wrappers (src/sht.jl:96-100, 181-185).
 # d_alm.alm::(nalm_loc, ncomp) ComplexF64 and d_map.pixels::(npix_loc, ncomp) Float64 are borrowed
@@ -155,6 +148,7 @@ function alm2map_fused!(d_alm, d_map; nthreads::Integer = 0)
     (size(d_alm.alm, 2) == size(d_map.pixels, 2)) || throw(DomainError(0, "Number of components must match."))
     comm = (d_alm.info.comm == d_map.info.comm) ? d_alm.info.comm : throw(DomainError(0, "Communicators must match"))
     p = plan_for(d_map.info.nside, d_alm.info.lmax, comm; thetatot = d_map.info.thetatot, phi0 = d_map.info.phi0)
+    check_shards(p, d_alm, d_map)
     check(ccall((:hpsht_alm2map, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Cint),
                 p.handle, d_alm.alm, d_map.pixels, size(d_alm.alm, 2), nthreads))
     d_map
@@ -164,10 +158,23 @@ function adjoint_alm2map_fused!(d_map, d_alm; nthreads::Integer = 0)
     (size(d_alm.alm, 2) == size(d_map.pixels, 2)) || throw(DomainError(0, "Number of components must match."))
     comm = (d_alm.info.comm == d_map.info.comm) ? d_alm.info.comm : throw(DomainError(0, "Communicators must match"))
     p = plan_for(d_map.info.nside, d_alm.info.lmax, comm; thetatot = d_map.info.thetatot, phi0 = d_map.info.phi0)
+    check_shards(p, d_alm, d_map)
     check(ccall((:hpsht_adjoint_alm2map, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Cint),
                 p.handle, d_map.pixels, d_alm.alm, size(d_alm.alm, 2), nthreads))
     d_alm
 end
+
+# Stream-ordered forms for device-resident shards (CUDA.jl CuArrays): `alm` / `pixels` are device pointers, the
+# transform is ordered after the work queued on `stream` (a CUstream / cudaStream_t) and does not block the host.
+function alm2map_async!(p::Plan, d_alm_ptr::Ptr{Float64}, d_pixels_ptr::Ptr{Float64}, ncomp::Integer, stream::Ptr{Cvoid})
+    check(ccall((:hpsht_alm2map_async, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Cvoid}),
+                p.handle, d_alm_ptr, d_pixels_ptr, ncomp, stream))
+end
+function adjoint_alm2map_async!(p::Plan, d_pixels_ptr::Ptr{Float64}, d_alm_ptr::Ptr{Float64}, ncomp::Integer, stream::Ptr{Cvoid})
+    check(ccall((:hpsht_adjoint_alm2map_async, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Cvoid}),
+                p.handle, d_pixels_ptr, d_alm_ptr, ncomp, stream))
+end
+synchronize(p::Plan) = check(ccall((:hpsht_plan_synchronize, lib), Cint, (Ptr{Cvoid},), p.handle))
 
 # Shards on the device (SURVEY 8f N1-N3).  Methods to add next to src/alm.jl:621-660, 693-713 and
 # src/cl.jl:33-38; `comp` arguments are 1-based columns of d_alm.alm as in the reference.
@@ -181,10 +188,16 @@ function dot_fused(a, b; comp1::Integer = 1, comp2::Integer = 1, nside::Integer)
     res[]
 end
 
-function almxfl_fused!(alm, fl::Vector{Float64}; nside::Integer)
+# almxfl!(alm, fl) (src/alm.jl:693-713): column c of `alm` is scaled by column c of `fl`, for the first
+# min(size(alm.alm, 2), size(fl, 2)) columns only -- a vector `fl` touches column 1 alone.
+function almxfl_fused!(alm, fl::AbstractVecOrMat{Float64}; nside::Integer)
     p = plan_for(nside, alm.info.lmax, alm.info.comm)
-    check(ccall((:hpsht_plan_almxfl, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Float64}, Int64, Cint),
-                p.handle, alm.alm, fl, length(fl), size(alm.alm, 2)))
+    ncol = min(size(alm.alm, 2), size(fl, 2))
+    for c in 1:ncol
+        flc = Vector{Float64}(fl[:, c])
+        check(ccall((:hpsht_plan_almxfl, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Float64}, Int64, Cint),
+                    p.handle, pointer(alm.alm, (c - 1) * size(alm.alm, 1) + 1), flc, length(flc), 1))
+    end
     alm
 end
 

@@ -171,9 +171,14 @@ class Plan:
         return r.value
 
     def almxfl(self, alm, fl, ncomp: int) -> None:
-        """almxfl!(d_alm, fl) (src/alm.jl:693-713): in place, every component, fl zero-extended."""
-        fl = np.ascontiguousarray(fl, dtype=np.float64)
-        _lib.check(_lib.lib().hpsht_plan_almxfl(self.handle, _lib.ptr(alm), _lib.ptr(fl), len(fl), ncomp))
+        """almxfl!(d_alm, fl) (src/alm.jl:693-713), in place.  Like the reference, column c of ``alm`` ([ncomp][nalm_loc])
+        is scaled by column c of ``fl`` for the first min(ncomp, ncol(fl)) columns only: a 1-D ``fl`` touches the first
+        component alone, ``fl`` of shape [ncol, n] scales ncol components, each by its own ``fl``, zero-extended to lmax + 1."""
+        fl = np.atleast_2d(np.ascontiguousarray(fl, dtype=np.float64))
+        base = _lib.ptr(alm)
+        for c in range(min(ncomp, fl.shape[0])):
+            flc = np.ascontiguousarray(fl[c])
+            _lib.check(_lib.lib().hpsht_plan_almxfl(self.handle, base + c * self.nalm_loc * 16, _lib.ptr(flc), len(flc), 1))
 
     def alm2cl(self, alm1, alm2=None) -> np.ndarray:
         """alm2cl(a[, b]) of one component each (src/cl.jl:5-38), summed over the ranks."""

@@ -164,6 +164,12 @@ int hpsht_plan_synchronize(hpsht_plan* plan);
    creation).  Off = the stages run back to back, which is what the per-stage timers want.  Must be set
    identically on every rank of the plan.                                                 */
 int hpsht_plan_set_dev_blocks(hpsht_plan* plan, int on);
+/* The ring blocks a plan of (nside, lmax, n_ranks) cuts (host arithmetic only, no device needed): nblocks and,
+   for block b and rank t, the range [lo[b*n_ranks + t], hi[b*n_ranks + t]) of rank t's local rings.  It takes
+   no rank argument: every rank of a collective call derives the same cut (and the same send / receive counts
+   per block) from these numbers.  lo / hi may be NULL; capacity = entries available in each.            */
+int hpsht_ring_block_ranges(int64_t nside, int64_t lmax, int n_ranks, int* nblocks, int64_t* lo, int64_t* hi,
+                            int capacity);
 
 /* ---- shards on the device: scatter / gather / algebra -------------------
    All collective over the plan's ranks; host or device pointers.  `ncomp` components are moved
@@ -183,8 +189,10 @@ int hpsht_plan_gather_map(hpsht_plan* plan, const double* map, double* global_ma
 /* dot(a, b) of one component each (nalm_loc complex128): weight 1 for m = 0 (real parts only), 2 for
    m > 0, summed over all ranks (localdot + Allreduce, src/alm.jl:621-660).                         */
 int hpsht_plan_dot(hpsht_plan* plan, const double* alm1, const double* alm2, double* result);
-/* almxfl!: alm[l, m] *= fl[l] on every component; fl has nfl entries and is zero-extended to lmax + 1
-   (src/alm.jl:693-713).                                                                            */
+/* almxfl! kernel: alm[l, m] *= fl[l] on `ncomp` consecutive components; fl has nfl entries and is zero-extended
+   to lmax + 1.  The reference (src/alm.jl:693-713) scales column c of the DAlm by column c of `fl` for the first
+   min(ncomp, ncol(fl)) columns only -- the bindings loop over those columns with ncomp = 1 and the column's pointer
+   (healpixmpi.jl_b200/sht.py Plan.almxfl, julia/HealpixMPIB200.jl almxfl_fused!).                    */
 int hpsht_plan_almxfl(hpsht_plan* plan, double* alm, const double* fl, int64_t nfl, int ncomp);
 /* alm2cl of one component each: cl[l] = sum_m w_m Re(a conj b) / (2l + 1), w = 1 (m = 0) or 2, summed
    over all ranks; cl has lmax + 1 entries (src/cl.jl:5-38).                                         */

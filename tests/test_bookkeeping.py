@@ -181,3 +181,28 @@ def test_no_cpu_fallback(H):
                 assert "oracle" not in txt.replace("oracle/", "").lower() or f == "__init__.py" or True
                 assert "import oracle" not in txt and "from oracle" not in txt and "liborc" not in txt \
                     and "cpu_port" not in txt, f
+
+
+@pytest.mark.parametrize("nside,P", [(1024, 3), (2048, 12), (4096, 1), (4096, 2), (4096, 8), (8192, 5), (64, 2), (1024, 7)])
+def test_ring_blocks_are_cut_from_rank_independent_quantities(H, nside, P):
+    """the block count of the pipelined calls was once chosen from the rank-LOCAL pixel count
+    (nside 1024, P 3: ranks 0/1 took 6 blocks, rank 2 one) and the ranks then issued different NCCL groups.  The cut
+    is now a function of (nside, lmax, P, environment) alone -- hpsht_ring_block_ranges takes no rank -- and every
+    rank's share of every block is a contiguous run of its local rings that tiles [0, nrings(rank))."""
+    L = H._lib.lib()
+    lmax = 2 * nside - 1
+    nb = C.c_int()
+    cap = 64 * P
+    lo = np.zeros(cap, dtype=np.int64)
+    hi = np.zeros(cap, dtype=np.int64)
+    H._lib.check(L.hpsht_ring_block_ranges(nside, lmax, P, C.byref(nb), lo.ctypes.data, hi.ctypes.data, cap))
+    nb = nb.value
+    big = 12 * nside * nside // P >= (1 << 22)
+    assert (nb > 1) == big, (nb, big)
+    lo, hi = lo[:nb * P].reshape(nb, P), hi[:nb * P].reshape(nb, P)
+    eq = 2 * nside
+    for t in range(P):
+        nr = H.get_nrings_RR(eq, t, P)
+        assert hi[0, t] == nr and lo[nb - 1, t] == 0            # pole-most block ends the local list, equator-most starts it
+        assert np.all(hi[1:, t] == lo[:-1, t]) and np.all(hi[:, t] >= lo[:, t])
+    assert int((hi - lo).sum()) == 4 * nside - 1

@@ -106,15 +106,18 @@ def test_dot_almxfl_alm2cl(Hm, nside, lmax):
         assert abs(got - ref) <= 1e-13 * abs(ref) + 1e-13
     # almxfl with a short fl (zero-extended, src/alm.jl:699-701)
     fl = rng.standard_normal(lmax - 3)
-    x = loc.copy()
-    plan.almxfl(x, fl, 2)
-    flx = np.concatenate([fl, np.zeros(lmax + 1 - len(fl))])
+    # the reference scales min(ncomp, ncol(fl)) columns: a vector fl touches the first component only
     mval, mstart0 = plan.alm_info()
-    ref = loc.copy()
-    for mi, m in enumerate(mval):
-        sl = slice(mstart0[mi] + m, mstart0[mi] + lmax + 1)
-        ref[:, sl] = loc[:, sl] * flx[m:]
-    assert np.array_equal(x, ref)
+    for fls in (fl[None, :], np.stack([fl, 2.0 * fl])):
+        x = loc.copy()
+        plan.almxfl(x, fls if fls.shape[0] > 1 else fl, 2)
+        ref = loc.copy()
+        for c in range(fls.shape[0]):
+            flx = np.concatenate([fls[c], np.zeros(lmax + 1 - fls.shape[1])])
+            for mi, m in enumerate(mval):
+                sl = slice(mstart0[mi] + m, mstart0[mi] + lmax + 1)
+                ref[c, sl] = loc[c, sl] * flx[m:]
+        assert np.array_equal(x, ref)
     # alm2cl (src/cl.jl:5-38)
     cl = plan.alm2cl(loc[0], loc[1])
     refcl = np.zeros(lmax + 1)
