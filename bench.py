@@ -56,6 +56,9 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_FULL_AFFINITY = None
+
+
 def bind_to_gpu_numa_node(torch, local_rank):
     """Launcher-side policy for the host-pointer (e2e) path: run this rank -- and first-touch its pinned buffers --
     on the NUMA node its GPU hangs off (all ranks on node 0 was the round-1 default; VERDICT r1 weak #6)."""
@@ -69,7 +72,9 @@ def bind_to_gpu_numa_node(torch, local_rank):
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
+        global _FULL_AFFINITY
+        _FULL_AFFINITY = os.sched_getaffinity(0)
+        cpus &= _FULL_AFFINITY
         if cpus:
             os.sched_setaffinity(0, cpus)
         return {"numa_node": node, "pci": bus, "cpus_bound": len(cpus)}
@@ -172,6 +177,8 @@ class CpuPort:
 
         self.P = P
         self.nside, self.lmax, self.transforms = nside, lmax, transforms
+        if _FULL_AFFINITY:  # the GPU arm bound this process to one NUMA node: the CPU arm gets the whole machine back
+            os.sched_setaffinity(0, _FULL_AFFINITY)
         # torchrun exports OMP_NUM_THREADS=1: ask for the machine explicitly and report what OpenMP grants
         P.set_threads(os.cpu_count() or 1)
         self.threads = P.max_threads()

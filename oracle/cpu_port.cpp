@@ -418,28 +418,51 @@ void run_m(int spin, const LegendreTables& T, const std::vector<Pair>& pairs, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// ring stage: plain recursive mixed-radix complex FFT (radix 2/3/5/generic, Bluestein above 64)
+// ring stage: plain recursive mixed-radix complex FFT (radix 4/2/3/5, generic odd radix up to 64); what is
+// left of n after the small factors are split off (a ring has n = 4 r with r often prime) goes through a
+// Bluestein convolution of that length only
 // ---------------------------------------------------------------------------------------------
 struct FftPlan {
   int64_t n = 0;
   std::vector<cd> w;          // exp(-2 pi i k / n)
-  // Bluestein (only when the largest prime factor is big)
-  bool blue = false;
-  int64_t M = 0;
+  int64_t leaf = 0;           // n with the factors 2, 3, 5 removed, when that has a prime factor > 64 (else 0)
+  int64_t M = 0;              // Bluestein length for the leaf (power of two >= 2 leaf - 1)
   std::vector<cd> chirp, chirpF;
-  FftPlan* sub = nullptr;
+  FftPlan* sub = nullptr;     // plan of length M
   ~FftPlan() { delete sub; }
 };
-void fft_rec(const FftPlan& P, const cd* in, int64_t istride, cd* out, int64_t n, int64_t wstride) {
+void fft_rec(const FftPlan& P, const cd* in, int64_t istride, cd* out, int64_t n, int64_t wstride, std::vector<cd>& work);
+// leaf DFT by Bluestein: out[k] = sum_j in[j istride] exp(-2 pi i jk / L)
+void bluestein_leaf(const FftPlan& P, const cd* in, int64_t istride, cd* out, std::vector<cd>& work) {
+  const int64_t L = P.leaf, M = P.M;
+  std::vector<cd> sub_work;
+  const size_t base = work.size();
+  work.resize(base + (size_t)(2 * M));
+  cd* a = work.data() + base;
+  cd* A = a + M;
+  for (int64_t k = 0; k < L; ++k) a[k] = in[k * istride] * P.chirp[(size_t)k];
+  for (int64_t k = L; k < M; ++k) a[k] = cd(0, 0);
+  fft_rec(*P.sub, a, 1, A, M, 1, sub_work);
+  for (int64_t k = 0; k < M; ++k) a[k] = std::conj(A[k] * P.chirpF[(size_t)k]);
+  fft_rec(*P.sub, a, 1, A, M, 1, sub_work);
+  const double inv = 1.0 / (double)M;
+  for (int64_t k = 0; k < L; ++k) out[k] = std::conj(A[k]) * inv * P.chirp[(size_t)k];
+  work.resize(base);
+}
+void fft_rec(const FftPlan& P, const cd* in, int64_t istride, cd* out, int64_t n, int64_t wstride, std::vector<cd>& work) {
   if (n == 1) {
     out[0] = in[0];
+    return;
+  }
+  if (P.leaf > 0 && n == P.leaf) {
+    bluestein_leaf(P, in, istride, out, work);
     return;
   }
   int64_t r = 0;
   for (int64_t p : {4, 2, 3, 5}) if (n % p == 0) { r = p; break; }
   if (r == 0) for (r = 7; n % r; r += 2) {}
   const int64_t mth = n / r;
-  for (int64_t k = 0; k < r; ++k) fft_rec(P, in + k * istride, istride * r, out + k * mth, mth, wstride * r);
+  for (int64_t k = 0; k < r; ++k) fft_rec(P, in + k * istride, istride * r, out + k * mth, mth, wstride * r, work);
   // decimation in time: X[q + mth*s] = sum_k W_n^{k q} W_r^{k s} Y_k[q]
   const cd* w = P.w.data();
   if (r == 2) {
@@ -479,47 +502,38 @@ FftPlan* make_plan(int64_t n) {
   const long double tp = 2.0L * LT_PI / (long double)n;
   P->w.resize((size_t)n);
   for (int64_t k = 0; k < n; ++k) P->w[(size_t)k] = cd((double)cosl(tp * k), (double)-sinl(tp * k));
-  int64_t big = 1, t = n;
-  for (int64_t p = 2; p * p <= t; ++p)
+  int64_t L = n;
+  for (int64_t p : {2, 3, 5})
+    while (L % p == 0) L /= p;
+  int64_t big = 1, t = L;
+  for (int64_t p = 7; p * p <= t; p += 2)
     while (t % p == 0) big = std::max(big, p), t /= p;
   big = std::max(big, t);
-  if (big > 64) {
-    P->blue = true;
+  if (L > 1 && big > 64) {
+    P->leaf = L;
     P->M = 1;
-    while (P->M < 2 * n - 1) P->M *= 2;
+    while (P->M < 2 * L - 1) P->M *= 2;
     P->sub = make_plan(P->M);
-    P->chirp.resize((size_t)n);
-    for (int64_t k = 0; k < n; ++k) {
-      const int64_t kk = (k * k) % (2 * n);
-      const long double a = LT_PI * (long double)kk / (long double)n;
+    P->chirp.resize((size_t)L);
+    for (int64_t k = 0; k < L; ++k) {
+      const int64_t kk = (k * k) % (2 * L);
+      const long double a = LT_PI * (long double)kk / (long double)L;
       P->chirp[(size_t)k] = cd((double)cosl(a), (double)-sinl(a));
     }
-    std::vector<cd> b((size_t)P->M, cd(0, 0));
-    for (int64_t k = 0; k < n; ++k) {
+    std::vector<cd> b((size_t)P->M, cd(0, 0)), wk;
+    for (int64_t k = 0; k < L; ++k) {
       b[(size_t)k] = std::conj(P->chirp[(size_t)k]);
       if (k) b[(size_t)(P->M - k)] = b[(size_t)k];
     }
     P->chirpF.resize((size_t)P->M);
-    fft_rec(*P->sub, b.data(), 1, P->chirpF.data(), P->M, 1);
+    fft_rec(*P->sub, b.data(), 1, P->chirpF.data(), P->M, 1, wk);
   }
   return P;
 }
 // forward DFT (e^{-i}); inverse via conjugation by the caller
 void fft_fwd(const FftPlan& P, const cd* in, cd* out, std::vector<cd>& work) {
-  if (!P.blue) {
-    fft_rec(P, in, 1, out, P.n, 1);
-    return;
-  }
-  const int64_t n = P.n, M = P.M;
-  work.assign((size_t)(2 * M), cd(0, 0));
-  cd* a = work.data();
-  cd* A = a + M;
-  for (int64_t k = 0; k < n; ++k) a[k] = in[k] * P.chirp[(size_t)k];
-  fft_rec(*P.sub, a, 1, A, M, 1);
-  for (int64_t k = 0; k < M; ++k) a[k] = std::conj(A[k] * P.chirpF[(size_t)k]);
-  fft_rec(*P.sub, a, 1, A, M, 1);
-  const double inv = 1.0 / (double)M;
-  for (int64_t k = 0; k < n; ++k) out[k] = std::conj(A[k]) * inv * P.chirp[(size_t)k];
+  work.clear();
+  fft_rec(P, in, 1, out, P.n, 1, work);
 }
 
 struct PlanCache {
