@@ -21,6 +21,32 @@
 #include <algorithm>
 #include <cmath>
 
+#ifdef HPSHT_FFT_PROFILE
+// phase-level cycle accounting of k_leg2map (build with -DHPSHT_FFT_PROFILE; tools/fft_profile.py)
+__device__ unsigned long long g_fft_prof[64];
+#define FFT_PROF_INIT() long long prof_t = clock64(); const int prof_c = (d.M == 0 ? 0 : (d.M > 4096 ? 1 : 2)) * 16
+#define FFT_PROF(i)                                                                   \
+  do {                                                                                \
+    __syncthreads();                                                                  \
+    if (threadIdx.x == 0) {                                                           \
+      const long long t2 = clock64();                                                 \
+      atomicAdd(&g_fft_prof[prof_c + (i)], (unsigned long long)(t2 - prof_t));        \
+      prof_t = t2;                                                                    \
+    }                                                                                 \
+  } while (0)
+extern "C" int hpsht_debug_fft_profile(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_fft_prof, sizeof(unsigned long long) * 64);
+  if (reset) {
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(g_fft_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#else
+#define FFT_PROF_INIT()
+#define FFT_PROF(i)
+#endif
+
 namespace hpsht {
 
 namespace {
@@ -332,10 +358,12 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
   const Roots W{S.hi, S.lo};
   const Tw TW{S.hi2, S.lo2, d.M ? d.M : d.r};
 
+  FFT_PROF_INIT();
   build_roots(S.hi, S.lo, n, 1.0, tid, nt);
   build_roots(S.hi2, S.lo2, d.M ? d.M : d.r, -1.0, tid, nt);
   __syncthreads();  // the phases below come from the root table
   const Phase PH(d, W);
+  FFT_PROF(0);
 
   // ---- phase shift + alias fold: X[k], k = 0..N ----
   {
@@ -380,6 +408,7 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
     }
   }
   __syncthreads();
+  FFT_PROF(1);
 
   // ---- X -> Zc (in place, pairs k <-> N-k) ----
   for (int k = tid; k <= r; k += nt) {
@@ -406,6 +435,7 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
     S.A[k + r] = cmul(csub(a, b), W(2 * k));
   }
   __syncthreads();
+  FFT_PROF(2);
 
   const double2* hhat = d.hoff >= 0 ? hhat_all + d.hoff : nullptr;
   double* out = map + (int64_t)comp * map_cstride + d.pixoff;
@@ -414,6 +444,7 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
     // power-of-two r: both halves transformed in place (DIF: results in bit-reversed order, read back
     // through the reversed index instead of a separate permutation pass), one fully coalesced store
     fft_dif<true>(S.A, r, TW, tid, nt, 2);
+    FFT_PROF(3);
     const int lgr = 31 - __clz(r);
     // ---- pixels: x[4j..4j+3] = Re U[j], Im U[j], Re V[j], Im V[j] ----
     if (al16) {
@@ -426,6 +457,7 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
         out[2 * t + 1] = v.y;
       }
     }
+    FFT_PROF(4);
   } else {
     // Bluestein: A becomes the work array, v waits in B.  U and V are stored as interleaved 16-byte
     // pieces (the two stores of a 32-byte sector meet in L2).
@@ -433,6 +465,7 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
     __syncthreads();
     for (int half = 0; half < 2; ++half) {
       idft_r(S.A, half == 0 ? S.A : S.B, r, d.M, hhat, W, TW, tid, nt);
+      FFT_PROF(3);
       if (al16) {
         double2* out2 = reinterpret_cast<double2*>(out);
         for (int j = tid; j < r; j += nt) out2[2 * j + half] = S.A[j];
@@ -443,6 +476,7 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
         }
       }
       __syncthreads();  // A is reused as the work array of the second half
+      FFT_PROF(4);
     }
   }
 }

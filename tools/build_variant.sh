@@ -10,7 +10,7 @@ mkdir -p "$out/obj_$name"
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fopenmp,-Wno-unknown-pragmas -ccbin /usr/bin/g++"
 for f in legendre ringfft api; do
   # ringfft / api objects are reused from the main build unless the flags name them
-  if [ "$f" = legendre ] || [ -n "$VARIANT_ALL" ]; then
+  if [ "$f" = "${VARIANT_FILE:-legendre}" ] || [ -n "$VARIANT_ALL" ]; then
     $NV "$@" -c "$src/$f.cu" -o "$out/obj_$name/$f.o" &
   else
     cp "$src/build/$f.o" "$out/obj_$name/$f.o"
