@@ -149,7 +149,7 @@ struct hpsht_plan {
   bool dev_blocks = true;               // P>1: device-pointer calls run block by block too (exchange overlap)
   std::vector<std::unique_ptr<RingFFT>> fftb;
   std::vector<int64_t> bj_lo, bj_hi;    // [block][rank]: local ring range of the block on that rank
-  std::vector<cudaEvent_t> ev_blk, ev_x, ev_f;
+  std::vector<cudaEvent_t> ev_blk, ev_x, ev_f, ev_alm;
   cudaEvent_t ev_hdone = nullptr, ev_a0 = nullptr, ev_a1 = nullptr, ev_entry = nullptr, ev_user = nullptr,
               ev_done = nullptr;
   int64_t blo(int set, int b, int t) const { return set ? bj_lo[(size_t)b * P + t] : 0; }
@@ -253,7 +253,11 @@ void hpsht_plan::ensure_stages() {
   }
   HP_CUDA(cudaStreamCreateWithPriority(&fstream, cudaStreamNonBlocking, prio_hi));
   HP_CUDA(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
-  HP_CUDA(cudaStreamCreateWithFlags(&ostream, cudaStreamNonBlocking));
+  // Several ranks of one host share its memory system: on the 8 x B200 box a rank's H2D runs at 21.5 GB/s alone but
+  // at 7.4 GB/s per direction when its D2H runs too (tools/h2d_bench.py, profiles/r02_multi_gpu.md) -- P > 1 keeps
+  // one copy stream so that the two directions take turns; a single rank gets one stream per direction.
+  if (P == 1) HP_CUDA(cudaStreamCreateWithFlags(&ostream, cudaStreamNonBlocking));
+  else ostream = hstream;
   for (cudaEvent_t* e : {&ev_hdone, &ev_a0, &ev_a1, &ev_entry, &ev_user, &ev_done})
     HP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   leg.setup(lmax, mval.data(), mstart.data(), nm_loc, nr_tot, thetatot.data(), lay, max_ncomp, stream);
@@ -277,7 +281,7 @@ void hpsht_plan::ensure_stages() {
 namespace {
 int wanted_ring_blocks(int64_t nside, int P) {
   const char* eb = getenv("HPSHT_HOST_BLOCKS");
-  int want = eb ? std::max(1, atoi(eb)) : (P <= 2 ? 6 : 4);
+  int want = eb ? std::max(1, atoi(eb)) : (P <= 2 ? 7 : 5);
   if (!eb && 12 * nside * nside / P < (1 << 22)) want = 1;  // small maps: the copies are microseconds
   return want;
 }
@@ -416,24 +420,34 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp, b
   }
   HP_CUDA(cudaEventRecord(e[0], stream));
   HP_CUDA(cudaEventRecord(ev_entry, stream));
-  for (cudaStream_t s : {cstream, fstream, hstream, ostream})
+  for (cudaStream_t s : {cstream, fstream, hstream, ostream != hstream ? ostream : (cudaStream_t) nullptr})
     if (s) HP_CUDA(cudaStreamWaitEvent(s, ev_entry, 0));
 
   const int spin = ncomp == 1 ? 0 : 2;
   const bool host_map = synthesis ? !out_dev : !in_dev;  // the map side travels over PCIe
-  const int set = (HB > 1 && (P > 1 ? (dev_blocks || host_map) : host_map)) ? 1 : 0;
+  // P > 1, device pointers: block by block in the synthesis (the exchange of a block hides behind the next block's
+  // Legendre kernels: -3 ... -9 % per transform on 2 and 8 GPUs), in one piece in the adjoint (there the per-block
+  // launches cost more than the hidden exchange saves: +0 ... +5 %; profiles/r02_multi_gpu.md).  Host maps always go
+  // block by block.  The choice depends on nothing rank-local besides the pointer kind, which all ranks must share.
+  const int set = (HB > 1 && (host_map || (P > 1 && dev_blocks && synthesis))) ? 1 : 0;
   const int NB = leg.nblocks(set);
   auto fftof = [&](int b) -> RingFFT& { return set ? *fftb[(size_t)b] : fft; };
   auto plo = [&](int b) { return pix_at(blo(set, b, rank)); };
   auto phi = [&](int b) { return pix_at(bhi(set, b, rank)); };
-  // the first synthesis block / last adjoint block (the polar one) only touches the local m's
-  // [0, mi_split): the rest of the alm copy overlaps that block's Legendre work
-  const int mi_split = NB > 1 ? leg.block_mi_end(set, 0, spin) : (int)nm_loc;
-  const bool split_alm = mi_split > 0 && mi_split < (int)nm_loc && !getenv("HPSHT_NO_ALM_STREAM");
-  // alm elements of the local m's [0, mi_split) form a prefix of every component
-  const size_t a_split = split_alm ? (size_t)(mstart[(size_t)mi_split] + mval[(size_t)mi_split]) : 0;
+  // Block b (pole -> equator) only touches the local m's [0, mie[b]) (m <= mlim of its rings): a host-side alm is
+  // streamed in / out in the matching m-ranges [mie[b-1], mie[b]), so that only the polar block's share of the alm
+  // copy (synthesis: before the first block; adjoint: after the last one) is not hidden behind Legendre work.
+  std::vector<int> mie((size_t)NB, (int)nm_loc);
+  for (int b = 0, hi = 0; b + 1 < NB; ++b) mie[(size_t)b] = hi = std::max(hi, leg.block_mi_end(set, b, spin));
+  const bool split_alm = NB > 1 && mie[0] < (int)nm_loc && !getenv("HPSHT_NO_ALM_STREAM");
+  auto a_at = [&](int mi) { return mi < (int)nm_loc ? (size_t)(mstart[(size_t)mi] + mval[(size_t)mi]) : (size_t)nalm_loc; };
   const bool stream_alm_in = synthesis && !in_dev && split_alm;
   const bool stream_alm_out = !synthesis && !out_dev && split_alm;
+  if ((stream_alm_in || stream_alm_out) && (int)ev_alm.size() < NB) {
+    const size_t have = ev_alm.size();
+    ev_alm.resize((size_t)NB);
+    for (size_t i = have; i < ev_alm.size(); ++i) HP_CUDA(cudaEventCreateWithFlags(&ev_alm[i], cudaEventDisableTiming));
+  }
 
   const double* d_in = in;
   double* d_out = out;
@@ -458,13 +472,14 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp, b
   if (synthesis) {
     // ---- alm in ----
     if (stream_alm_in) {
-      for (int part = 0; part < 2; ++part) {
-        for (int c = 0; c < ncomp; ++c) {
-          const size_t o = ((size_t)c * nalm_loc + (part ? a_split : 0)) * 2;
-          const size_t n = (part ? (size_t)nalm_loc - a_split : a_split) * 2;
-          HP_CUDA(cudaMemcpyAsync(stage_alm.p + o, in + o, n * sizeof(double), cudaMemcpyHostToDevice, hstream));
-        }
-        HP_CUDA(cudaEventRecord(part ? ev_a1 : ev_a0, hstream));
+      for (int b = 0; b < NB; ++b) {
+        const size_t lo = a_at(b ? mie[(size_t)b - 1] : 0), hi = a_at(mie[(size_t)b]);
+        if (hi > lo)
+          for (int c = 0; c < ncomp; ++c) {
+            const size_t o = ((size_t)c * nalm_loc + lo) * 2;
+            HP_CUDA(cudaMemcpyAsync(stage_alm.p + o, in + o, (hi - lo) * 2 * sizeof(double), cudaMemcpyHostToDevice, hstream));
+          }
+        HP_CUDA(cudaEventRecord(ev_alm[(size_t)b], hstream));
       }
     } else if (!in_dev) {
       HP_CUDA(cudaMemcpyAsync(stage_alm.p, in, alm_d * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -472,16 +487,11 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp, b
     HP_CUDA(cudaEventRecord(e[1], stream));
     // ---- alm2leg (src/sht.jl:85), block by block ----
     leg.alm2leg_zero(legA, P == 1 ? (int64_t)max_ncomp * nr_loc * nm_tot : aoff[(size_t)P], ncomp, stream);
-    if (stream_alm_in) {
-      HP_CUDA(cudaStreamWaitEvent(stream, ev_a0, 0));
-      leg.alm2leg_prep(d_in, nalm_loc, ncomp, 0, mi_split, stream);
-    } else {
-      leg.alm2leg_prep(d_in, nalm_loc, ncomp, 0, (int)nm_loc, stream);
-    }
+    if (!stream_alm_in) leg.alm2leg_prep(d_in, nalm_loc, ncomp, 0, (int)nm_loc, stream);
     for (int b = 0; b < NB; ++b) {
-      if (b == 1 && stream_alm_in) {
-        HP_CUDA(cudaStreamWaitEvent(stream, ev_a1, 0));
-        leg.alm2leg_prep(d_in, nalm_loc, ncomp, mi_split, (int)nm_loc, stream);
+      if (stream_alm_in) {  // the m-range this block is the first to need
+        HP_CUDA(cudaStreamWaitEvent(stream, ev_alm[(size_t)b], 0));
+        leg.alm2leg_prep(d_in, nalm_loc, ncomp, b ? mie[(size_t)b - 1] : 0, mie[(size_t)b], stream);
       }
       leg.alm2leg_block(set, b, legA, ncomp, stream, b == NB - 1);
       if (b == NB - 1) HP_CUDA(cudaEventRecord(e[2], stream));
@@ -531,18 +541,22 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp, b
   } else {
     HP_CUDA(cudaEventRecord(e[1], stream));
     leg.leg2alm_begin(ncomp, stream);
-    // the local m's >= mi_split are complete before the last (polar) block starts: post-process them on the
-    // compute stream right there (a ~1 ms kernel) and copy them out while that block computes
-    auto early_alm_out = [&]() {
-      leg.leg2alm_end(d_out, nalm_loc, ncomp, stream, mi_split, (int)nm_loc);
-      HP_CUDA(cudaEventRecord(ev_a1, stream));
-      HP_CUDA(cudaStreamWaitEvent(ostream, ev_a1, 0));
+    // once block b is through, the blocks still to come (b-1 .. 0) only touch the local m's below mie[b-1]: the
+    // rows from there up to what has gone out already are final -- post-process them and copy them out on the
+    // output stream while the next block computes
+    int alm_done_from = (int)nm_loc;
+    auto alm_out_after = [&](int b) {
+      const int lo = b ? mie[(size_t)b - 1] : 0;
+      if (lo >= alm_done_from) return;
+      HP_CUDA(cudaEventRecord(ev_alm[(size_t)b], stream));
+      HP_CUDA(cudaStreamWaitEvent(ostream, ev_alm[(size_t)b], 0));
+      leg.leg2alm_end(d_out, nalm_loc, ncomp, ostream, lo, alm_done_from);
       for (int c = 0; c < ncomp; ++c) {
-        const size_t o = ((size_t)c * nalm_loc + a_split) * 2;
-        HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, ((size_t)nalm_loc - a_split) * 2 * sizeof(double),
+        const size_t o = ((size_t)c * nalm_loc + a_at(lo)) * 2;
+        HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, (a_at(alm_done_from) - a_at(lo)) * 2 * sizeof(double),
                                 cudaMemcpyDeviceToHost, ostream));
       }
-      HP_CUDA(cudaEventRecord(ev_hdone, ostream));
+      alm_done_from = lo;
     };
     // the small equator-most blocks go first so that the compute starts early
     for (int b = NB - 1; b >= 0; --b) {
@@ -582,17 +596,14 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp, b
         if (b == NB - 1) HP_CUDA(cudaEventRecord(e[3], cstream));
         HP_CUDA(cudaStreamWaitEvent(stream, ev_x[(size_t)b], 0));
       }
-      if (b == 0 && stream_alm_out) early_alm_out();
       leg.leg2alm_block(set, b, legA, ncomp, stream, b == 0);  // leg2alm (src/sht.jl:178)
+      if (stream_alm_out) alm_out_after(b);
     }
-    leg.leg2alm_end(d_out, nalm_loc, ncomp, stream, 0, stream_alm_out ? mi_split : (int)nm_loc);
+    if (!stream_alm_out) leg.leg2alm_end(d_out, nalm_loc, ncomp, stream, 0, (int)nm_loc);
     HP_CUDA(cudaEventRecord(e[4], stream));
     // ---- alm out ----
     if (stream_alm_out) {
-      for (int c = 0; c < ncomp; ++c) {
-        const size_t o = (size_t)c * nalm_loc * 2;
-        HP_CUDA(cudaMemcpyAsync(out + o, d_out + o, a_split * 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
-      }
+      HP_CUDA(cudaEventRecord(ev_hdone, ostream));
       HP_CUDA(cudaStreamWaitEvent(stream, ev_hdone, 0));
     } else if (!out_dev) {
       HP_CUDA(cudaMemcpyAsync(out, d_out, alm_d * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -616,7 +627,7 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp, b
 
 void hpsht_plan::synchronize() {
   HP_CUDA(cudaSetDevice(device));
-  for (cudaStream_t s : {stream, cstream, fstream, hstream, ostream})
+  for (cudaStream_t s : {stream, cstream, fstream, hstream, ostream != hstream ? ostream : (cudaStream_t) nullptr})
     if (s) HP_CUDA(cudaStreamSynchronize(s));
   if (times_pending) finish_times();
 }
@@ -1021,10 +1032,11 @@ int hpsht_plan_destroy(hpsht_plan* plan) {
   return guarded([&] {
     if (!plan) return;
     cudaSetDevice(plan->device);
+    if (plan->ostream == plan->hstream) plan->ostream = nullptr;
     for (cudaStream_t st : {plan->stream, plan->cstream, plan->fstream, plan->hstream, plan->ostream})
       if (st) cudaStreamSynchronize(st);
     if (plan->comm) NcclApi::get().CommDestroy(plan->comm);
-    for (auto* v : {&plan->ev_blk, &plan->ev_x, &plan->ev_f})
+    for (auto* v : {&plan->ev_blk, &plan->ev_x, &plan->ev_f, &plan->ev_alm})
       for (auto& e : *v) cudaEventDestroy(e);
     for (cudaEvent_t e : {plan->ev_hdone, plan->ev_a0, plan->ev_a1, plan->ev_entry, plan->ev_user, plan->ev_done})
       if (e) cudaEventDestroy(e);

@@ -1374,17 +1374,36 @@ std::vector<int> cut_ring_blocks(const std::vector<PairHost>& pairs, int want, c
   if (want < 1) want = 1;
   bp.push_back(0);
   // Preferred cut: multiples of the least common multiple of the kernels' tile sizes (512 pairs), so that
-  // no block ends in a partly filled tile and no accuracy class is cut inside a tile.  The equator-most
-  // block -- whose copy cannot hide behind compute -- is a single unit (6 % of the pixels at nside 4096);
-  // the other want-1 blocks share the rest (nside 4096, want 6: 5 x 1536 + 512 pairs).
+  // no block ends in a partly filled tile and no accuracy class is cut inside a tile.  Block sizes grow from
+  // both ends towards the middle (1, 2, 3, ... units): what a pipelined call cannot hide is the polar block's
+  // share of the alm copy and the equator-most block's map copy, and a block's copy must fit behind the
+  // compute of its (smaller) neighbour towards the end (nside 4096, want 7: 512 1024 1536 2048 1536 1024 512).
   int64_t align = 32;
   for (int t : {syn_tile(0, LK_STD), syn_tile(2, LK_STD), adj_tile(0), adj_tile(2)}) align = align / gcd_i(align, t) * t;
   if (want > 1 && np >= 2 * align) {
     const int64_t units = (np + align - 1) / align;  // last unit may be partial
-    const int64_t nb = std::min<int64_t>(want - 1, units - 1);
-    for (int64_t b = 1; b <= nb; ++b) {
-      const int64_t p = ((units - 1) * b / nb) * align;
-      if (p > bp.back() && p < np) bp.push_back((int)p);
+    std::vector<int64_t> left, right;
+    int64_t rem = units;
+    for (int64_t k = 1; (int64_t)(left.size() + right.size()) + 3 <= want && rem >= 2 * k + 1; ++k) {
+      left.push_back(k);
+      right.push_back(k);
+      rem -= 2 * k;
+    }
+    if (left.empty() && units >= 2) {  // want == 2: everything but the equator-most unit, then that unit
+      left.push_back(units - 1);
+      rem = 1;
+    } else if (rem > 0) {
+      left.push_back(rem);
+      rem = 0;
+    }
+    int64_t at = 0;
+    for (int64_t u : left) {
+      at += u;
+      if (at * align < np) bp.push_back((int)(at * align));
+    }
+    for (size_t i = right.size(); i-- > 0;) {
+      at += right[i];
+      if (at * align < np && (int)(at * align) > bp.back()) bp.push_back((int)(at * align));
     }
   } else if (want > 1) {
     // small problems (tests): equal-weight blocks on warp-aligned boundaries

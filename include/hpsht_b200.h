@@ -142,7 +142,9 @@ int hpsht_plan_map_info(const hpsht_plan* plan, int64_t* rings /*1-based ids*/,
                         double* phi0, double* thetatot /*[nring_tot]*/);
 
 /* alm (nalm_loc, ncomp) complex128 -> map (npix_loc, ncomp) float64.  Host or device
-   pointers (see top).  Collective.  With device pointers: the library waits for the device on entry
+   pointers (see top).  Collective: every rank of the plan calls it, and every rank passes the SAME KIND of
+   pointer for `map` (all host or all device) -- the pipeline a call runs (how many NCCL exchanges it issues)
+   depends on it, a mix would dead-lock.  With device pointers: the library waits for the device on entry
    (the caller's producer stream is unknown to it; its own streams are non-blocking) and the call is
    complete on return.                                                                  */
 int hpsht_alm2map(hpsht_plan* plan, const double* alm, double* map, int ncomp, int nthreads);
