@@ -202,16 +202,17 @@ void block_s0(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool ysin,
       const double sg = (ALT && (n & 1)) ? -1.0 : 1.0;
       if (ADJ) {
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        for (int w = 0; w < W; ++w) {
-          if (any0) {
+        if (any0) {
+#pragma omp simd reduction(+ : s0, s1, s2, s3)
+          for (int w = 0; w < W; ++w) {
             const double pv = sg * u[w];
-            s0 = std::fma(pv, er[w], s0);
-            s1 = std::fma(pv, ei[w], s1);
-            s2 = std::fma(pv, orr[w], s2);
-            s3 = std::fma(pv, oi[w], s3);
+            s0 += pv * er[w];
+            s1 += pv * ei[w];
+            s2 += pv * orr[w];
+            s3 += pv * oi[w];
           }
-          rec_step<DIFF>(std::fma(a_, y[w], b_), u[w], v[w]);
         }
+        for (int w = 0; w < W; ++w) rec_step<DIFF>(std::fma(a_, y[w], b_), u[w], v[w]);
         double* d = &acc[4 * n];
         d[0] += s0, d[1] += s1, d[2] += s2, d[3] += s3;
       } else {
@@ -317,17 +318,23 @@ void block_s2(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool yform
       const double sgn = (odd0 ^ ((j & 1) != 0)) ? -1.0 : 1.0;
       double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
       const double* s = ADJ ? nullptr : &stream[4 * j];
+      if (ADJ && any0) {
+        const double* ap = reinterpret_cast<const double*>(wpN);   // (re, im) pairs
+        const double* bp = reinterpret_cast<const double*>(wpS);
+        const double* cp2 = reinterpret_cast<const double*>(wmN);
+        const double* dp = reinterpret_cast<const double*>(wmS);
+#pragma omp simd reduction(+ : s0, s1, s2, s3)
+        for (int w = 0; w < W; ++w) {
+          const double sm_ = sgn * um[w], sp_ = sgn * up[w];
+          s0 += up[w] * ap[2 * w] + sm_ * bp[2 * w];
+          s1 += up[w] * ap[2 * w + 1] + sm_ * bp[2 * w + 1];
+          s2 += um[w] * cp2[2 * w] + sp_ * dp[2 * w];
+          s3 += um[w] * cp2[2 * w + 1] + sp_ * dp[2 * w + 1];
+        }
+      }
       for (int w = 0; w < W; ++w) {
         if (any0) {
           if (ADJ) {
-            s0 = std::fma(up[w], wpN[w].real(), s0);
-            s1 = std::fma(up[w], wpN[w].imag(), s1);
-            s0 = std::fma(sgn * um[w], wpS[w].real(), s0);
-            s1 = std::fma(sgn * um[w], wpS[w].imag(), s1);
-            s2 = std::fma(um[w], wmN[w].real(), s2);
-            s3 = std::fma(um[w], wmN[w].imag(), s3);
-            s2 = std::fma(sgn * up[w], wmS[w].real(), s2);
-            s3 = std::fma(sgn * up[w], wmS[w].imag(), s3);
           } else {
             PpN[w] = cd(std::fma(up[w], s[0], PpN[w].real()), std::fma(up[w], s[1], PpN[w].imag()));
             PmN[w] = cd(std::fma(um[w], s[2], PmN[w].real()), std::fma(um[w], s[3], PmN[w].imag()));
