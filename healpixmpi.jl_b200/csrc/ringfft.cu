@@ -18,6 +18,8 @@
 // Rings are grouped by size class (threads / shared memory per CTA) at plan time.
 #include "ringfft.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 
@@ -25,6 +27,7 @@
 // phase-level cycle accounting of k_leg2map (build with -DHPSHT_FFT_PROFILE; tools/fft_profile.py)
 __device__ unsigned long long g_fft_prof[64];
 #define FFT_PROF_INIT() long long prof_t = clock64(); const int prof_c = (d.M == 0 ? 0 : (d.M > 4096 ? 1 : 2)) * 16
+#define FFT_PROF_INIT_C(c) long long prof_t = clock64(); const int prof_c = (c) * 16
 #define FFT_PROF(i)                                                                   \
   do {                                                                                \
     __syncthreads();                                                                  \
@@ -44,6 +47,7 @@ extern "C" int hpsht_debug_fft_profile(unsigned long long* out, int reset) {
 }
 #else
 #define FFT_PROF_INIT()
+#define FFT_PROF_INIT_C(c)
 #define FFT_PROF(i)
 #endif
 
@@ -129,7 +133,9 @@ struct Phase {
   __device__ __forceinline__ double2 operator()(int m) const {
     if (pq < 0) return phase(m, phi0);
     if (pq == 0) return make_double2(1.0, 0.0);
-    const unsigned t = (unsigned)(((unsigned long long)(unsigned)m * (unsigned)pq) % n2);
+    // HEALPix rings have pq = 1 and, for m < 2n, no reduction at all (the 64-bit modulo costs more than the rest)
+    const unsigned t = pq == 1 ? ((unsigned)m < n2 ? (unsigned)m : (unsigned)m % n2)
+                               : (unsigned)(((unsigned long long)(unsigned)m * (unsigned)pq) % n2);
     const double2 w = W((int)(t >> 1));
     return (t & 1u) ? cmul(w, c1) : w;
   }
@@ -146,11 +152,19 @@ struct Phase {
 // then hits eight distinct 4-bank groups in EVERY radix-4 pass (quarter lengths 1, 4, 16, ...), where the plain
 // layout is 4-way (q = 1) and 2-way (q = 4) conflicted -- tools/proto/fft_bank_model.py reproduces the 36 %
 // replay excess ncu reports for M = 8192 and shows 0 % with this map.
-template <bool SWZ>
-__device__ __forceinline__ int swz(int i) { return SWZ ? (i ^ ((i >> 2) & 7)) : i; }
+// SWZ = 2 (half-ring kernels of the power-of-two rings, length 2^lg >= 256) also folds the TOP three index bits in:
+// the bit-reversed reads / writes that replace a reorder pass touch eight elements a multiple of 2^(lg-3) apart,
+// which the plain layout and SWZ = 1 put into one 4-bank group (8-way conflict); with the top bits in the XOR they
+// fall into eight distinct groups, and every pattern SWZ = 1 serves stays conflict free (the top bits are constant
+// within a quarter-warp there).  ncu before: 48 % of the shared-memory wavefronts of these kernels were replays.
+template <int SWZ>
+__device__ __forceinline__ int swz(int i, int lg = 0) {
+  return SWZ == 1 ? (i ^ ((i >> 2) & 7))
+                  : (SWZ == 2 ? (i ^ (((i >> 2) ^ (i >> (lg - 3))) & 7)) : (SWZ == 3 ? (i ^ ((i >> 4) & 7)) : i));
+}
 
 // `nb` transforms of length M stored back to back (buf + b * M) advance through the passes together
-template <bool INV, bool SWZ = false>
+template <bool INV, int SWZ = 0>
 __device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt, int nb = 1) {
   if (M < 2) return;
   const int lg = 31 - __clz(M);
@@ -161,9 +175,9 @@ __device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt, int 
     for (int t = tid; t < h * nb; t += nt) {
       const int i = t & (h - 1);
       double2* p = buf + (t >> (lg - 1)) * M;
-      const double2 a = p[swz<SWZ>(i)], b = p[swz<SWZ>(i + h)];
-      p[swz<SWZ>(i)] = cadd(a, b);
-      p[swz<SWZ>(i + h)] = cmul(csub(a, b), tw.get<INV>(i * ts));
+      const double2 a = p[swz<SWZ>(i, lg)], b = p[swz<SWZ>(i + h, lg)];
+      p[swz<SWZ>(i, lg)] = cadd(a, b);
+      p[swz<SWZ>(i + h, lg)] = cmul(csub(a, b), tw.get<INV>(i * ts));
     }
     L >>= 1;
     __syncthreads();
@@ -177,7 +191,7 @@ __device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt, int 
       double2* p = buf + (t >> (lg - 2)) * M;
       const int j = i & (q - 1);
       const int b = ((i >> lq) * L) + j;
-      const int i0 = swz<SWZ>(b), i1 = swz<SWZ>(b + q), i2 = swz<SWZ>(b + 2 * q), i3 = swz<SWZ>(b + 3 * q);
+      const int i0 = swz<SWZ>(b, lg), i1 = swz<SWZ>(b + q, lg), i2 = swz<SWZ>(b + 2 * q, lg), i3 = swz<SWZ>(b + 3 * q, lg);
       const double2 x0 = p[i0], x1 = p[i1], x2 = p[i2], x3 = p[i3];
       const double2 w1 = tw.get<INV>(j * ts);
       const double2 w2 = make_double2(fma(w1.x, w1.x, -w1.y * w1.y), 2.0 * w1.x * w1.y);  // w1^2
@@ -193,7 +207,7 @@ __device__ void fft_dif(double2* buf, int M, const Tw& tw, int tid, int nt, int 
   }
 }
 
-template <bool INV, bool SWZ = false>
+template <bool INV, int SWZ = 0>
 __device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt, int nb = 1) {
   if (M < 2) return;
   const int lg = 31 - __clz(M);
@@ -202,7 +216,7 @@ __device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt, int 
     for (int t = tid; t < (M >> 1) * nb; t += nt) {
       const int i = t & ((M >> 1) - 1);
       double2* p = buf + (t >> (lg - 1)) * M;
-      const int ia = swz<SWZ>(2 * i), ib = swz<SWZ>(2 * i + 1);
+      const int ia = swz<SWZ>(2 * i, lg), ib = swz<SWZ>(2 * i + 1, lg);
       const double2 a = p[ia], b = p[ib];
       p[ia] = cadd(a, b);
       p[ib] = csub(a, b);
@@ -220,7 +234,7 @@ __device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt, int 
       double2* p = buf + (t >> (lg - 2)) * M;
       const int j = i & (q - 1);
       const int b = ((i >> lq) * L) + j;
-      const int i0 = swz<SWZ>(b), i1 = swz<SWZ>(b + q), i2 = swz<SWZ>(b + 2 * q), i3 = swz<SWZ>(b + 3 * q);
+      const int i0 = swz<SWZ>(b, lg), i1 = swz<SWZ>(b + q, lg), i2 = swz<SWZ>(b + 2 * q, lg), i3 = swz<SWZ>(b + 3 * q, lg);
       const double2 x0 = p[i0], x1 = p[i1], x2 = p[i2], x3 = p[i3];
       const double2 w1 = tw.get<INV>(j * ts);
       const double2 w2 = make_double2(fma(w1.x, w1.x, -w1.y * w1.y), 2.0 * w1.x * w1.y);  // w1^2
@@ -234,6 +248,185 @@ __device__ void fft_dit(double2* buf, int M, const Tw& tw, int tid, int nt, int 
       p[i3] = csub(a1, s3);
     }
     __syncthreads();
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// radix-16 passes for the Bluestein work array (M >= 256): four fused radix-2 stages per trip through shared
+// memory instead of two -- a 8192-point transform is 1 radix-2 + 3 radix-16 passes instead of 1 + 6 radix-4 ones.
+// Any grouping of in-place radix-2 stages gives the same (bit-reversed) DIF output order, so these transforms
+// are interchangeable with fft_dif / fft_dit and the chirp spectrum table keeps its order.  Layout: swz<3>
+// (i ^ ((i >> 4) & 7)): the stride-16 accesses of the smallest pass and every contiguous access are conflict free.
+// ------------------------------------------------------------------------------------------------
+template <bool INV>
+__device__ __forceinline__ void bf4_dif(double2& x0, double2& x1, double2& x2, double2& x3, double2 w1, double2 w2) {
+  const double2 a0 = cadd(x0, x2), a2 = cmul(csub(x0, x2), w1);
+  const double2 a1 = cadd(x1, x3), a3 = mul_pm_i<INV>(cmul(csub(x1, x3), w1));
+  x0 = cadd(a0, a1);
+  x1 = cmul(csub(a0, a1), w2);
+  x2 = cadd(a2, a3);
+  x3 = cmul(csub(a2, a3), w2);
+}
+template <bool INV>
+__device__ __forceinline__ void bf4_dit(double2& x0, double2& x1, double2& x2, double2& x3, double2 w1, double2 w2) {
+  const double2 t1 = cmul(x1, w2), t3 = cmul(x3, w2);
+  const double2 a0 = cadd(x0, t1), a1 = csub(x0, t1);
+  const double2 a2 = cadd(x2, t3), a3 = csub(x2, t3);
+  const double2 s2 = cmul(a2, w1), s3 = mul_pm_i<INV>(cmul(a3, w1));
+  x0 = cadd(a0, s2);
+  x2 = csub(a0, s2);
+  x1 = cadd(a1, s3);
+  x3 = csub(a1, s3);
+}
+__device__ __forceinline__ double2 csqr(double2 w) { return make_double2(fma(w.x, w.x, -w.y * w.y), 2.0 * w.x * w.y); }
+// exp(-2 pi i c / 16) (INV: conjugated), c = 1, 2, 3
+template <bool INV>
+__device__ __forceinline__ double2 w16(int c) {
+  const double C1 = 0.92387953251128675613, S1 = 0.38268343236508977173, H = 0.70710678118654752440;
+  const double2 v = c == 1 ? make_double2(C1, -S1) : (c == 2 ? make_double2(H, -H) : make_double2(S1, -C1));
+  return INV ? make_double2(v.x, -v.y) : v;
+}
+
+template <bool INV>
+__device__ void dif_pass16(double2* buf, int M, int L, const Tw& tw, int tid, int nt) {
+  const int q = L >> 2, q1 = L >> 4, lq1 = 31 - __clz(q1), ts = tw.T / L;
+  for (int t = tid; t < (M >> 4); t += nt) {
+    const int j = t & (q1 - 1), base = ((t >> lq1) * L) + j;
+    double2 e[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) e[a][c] = buf[swz<3>(base + a * q + c * q1)];
+    const double2 wj = tw.get<INV>(j * ts);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double2 w1 = c == 0 ? wj : cmul(wj, w16<INV>(c));
+      bf4_dif<INV>(e[0][c], e[1][c], e[2][c], e[3][c], w1, csqr(w1));
+    }
+    const double2 wj4 = csqr(csqr(wj)), wj8 = csqr(wj4);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) bf4_dif<INV>(e[a][0], e[a][1], e[a][2], e[a][3], wj4, wj8);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) buf[swz<3>(base + a * q + c * q1)] = e[a][c];
+  }
+  __syncthreads();
+}
+template <bool INV>
+__device__ void dit_pass16(double2* buf, int M, int L, const Tw& tw, int tid, int nt) {
+  const int q = L >> 2, q1 = L >> 4, lq1 = 31 - __clz(q1), ts = tw.T / L;
+  for (int t = tid; t < (M >> 4); t += nt) {
+    const int j = t & (q1 - 1), base = ((t >> lq1) * L) + j;
+    double2 e[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) e[a][c] = buf[swz<3>(base + a * q + c * q1)];
+    const double2 wj = tw.get<INV>(j * ts);
+    const double2 wj4 = csqr(csqr(wj)), wj8 = csqr(wj4);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) bf4_dit<INV>(e[a][0], e[a][1], e[a][2], e[a][3], wj4, wj8);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double2 w1 = c == 0 ? wj : cmul(wj, w16<INV>(c));
+      bf4_dit<INV>(e[0][c], e[1][c], e[2][c], e[3][c], w1, csqr(w1));
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) buf[swz<3>(base + a * q + c * q1)] = e[a][c];
+  }
+  __syncthreads();
+}
+// single radix-2 / radix-4 passes at block length L (the stages left over when log2 M is not a multiple of 4;
+// they run at the LARGE block lengths, where every access is contiguous)
+template <bool INV>
+__device__ void dif_pass2(double2* buf, int M, int L, const Tw& tw, int tid, int nt) {
+  const int h = L >> 1, lh = 31 - __clz(h), ts = tw.T / L;
+  for (int t = tid; t < (M >> 1); t += nt) {
+    const int i = t & (h - 1), b = ((t >> lh) * L) + i;
+    const int ia = swz<3>(b), ib = swz<3>(b + h);
+    const double2 a = buf[ia], c = buf[ib];
+    buf[ia] = cadd(a, c);
+    buf[ib] = cmul(csub(a, c), tw.get<INV>(i * ts));
+  }
+  __syncthreads();
+}
+template <bool INV>
+__device__ void dit_pass2(double2* buf, int M, int L, const Tw& tw, int tid, int nt) {
+  const int h = L >> 1, lh = 31 - __clz(h), ts = tw.T / L;
+  for (int t = tid; t < (M >> 1); t += nt) {
+    const int i = t & (h - 1), b = ((t >> lh) * L) + i;
+    const int ia = swz<3>(b), ib = swz<3>(b + h);
+    const double2 a = buf[ia], c = cmul(buf[ib], tw.get<INV>(i * ts));
+    buf[ia] = cadd(a, c);
+    buf[ib] = csub(a, c);
+  }
+  __syncthreads();
+}
+template <bool INV>
+__device__ void dif_pass4(double2* buf, int M, int L, const Tw& tw, int tid, int nt) {
+  const int q = L >> 2, lq = 31 - __clz(q), ts = tw.T / L;
+  for (int t = tid; t < (M >> 2); t += nt) {
+    const int j = t & (q - 1), b = ((t >> lq) * L) + j;
+    const int i0 = swz<3>(b), i1 = swz<3>(b + q), i2 = swz<3>(b + 2 * q), i3 = swz<3>(b + 3 * q);
+    double2 x0 = buf[i0], x1 = buf[i1], x2 = buf[i2], x3 = buf[i3];
+    const double2 w1 = tw.get<INV>(j * ts);
+    bf4_dif<INV>(x0, x1, x2, x3, w1, csqr(w1));
+    buf[i0] = x0;
+    buf[i1] = x1;
+    buf[i2] = x2;
+    buf[i3] = x3;
+  }
+  __syncthreads();
+}
+template <bool INV>
+__device__ void dit_pass4(double2* buf, int M, int L, const Tw& tw, int tid, int nt) {
+  const int q = L >> 2, lq = 31 - __clz(q), ts = tw.T / L;
+  for (int t = tid; t < (M >> 2); t += nt) {
+    const int j = t & (q - 1), b = ((t >> lq) * L) + j;
+    const int i0 = swz<3>(b), i1 = swz<3>(b + q), i2 = swz<3>(b + 2 * q), i3 = swz<3>(b + 3 * q);
+    double2 x0 = buf[i0], x1 = buf[i1], x2 = buf[i2], x3 = buf[i3];
+    const double2 w1 = tw.get<INV>(j * ts);
+    bf4_dit<INV>(x0, x1, x2, x3, w1, csqr(w1));
+    buf[i0] = x0;
+    buf[i1] = x1;
+    buf[i2] = x2;
+    buf[i3] = x3;
+  }
+  __syncthreads();
+}
+// M = 2^lg >= 16, array in the swz<3> layout.  DIF: natural in, bit-reversed out.  DIT: the reverse.
+// skip_lead2: the caller has already done the leading radix-2 stage (only meaningful when log2 M is odd)
+template <bool INV>
+__device__ void fft_dif16(double2* buf, int M, const Tw& tw, int tid, int nt, bool skip_lead2 = false) {
+  const int rem = (31 - __clz(M)) & 3;
+  int L = M;
+  if (rem & 1) {
+    if (!skip_lead2) dif_pass2<INV>(buf, M, L, tw, tid, nt);
+    L >>= 1;
+  }
+  if (rem & 2) {
+    dif_pass4<INV>(buf, M, L, tw, tid, nt);
+    L >>= 2;
+  }
+  for (; L >= 16; L >>= 4) dif_pass16<INV>(buf, M, L, tw, tid, nt);
+}
+template <bool INV>
+__device__ void fft_dit16(double2* buf, int M, const Tw& tw, int tid, int nt) {
+  const int rem = (31 - __clz(M)) & 3;
+  const int Ltop = M >> ((rem & 1) + (rem & 2));   // block length the radix-16 passes end at
+  for (int L = 16; L <= Ltop; L <<= 4) dit_pass16<INV>(buf, M, L, tw, tid, nt);
+  int L = Ltop;
+  if (rem & 2) {
+    L <<= 2;
+    dit_pass4<INV>(buf, M, L, tw, tid, nt);
+  }
+  if (rem & 1) {
+    L <<= 1;
+    dit_pass2<INV>(buf, M, L, tw, tid, nt);
   }
 }
 
@@ -255,22 +448,29 @@ __device__ void bitrev_permute(double2* buf, int M, int tid, int nt) {
 
 // U[j] = sum_k src[k] exp(+2 pi i jk / r), j,k < r.
 //   power-of-two r (M == 0): in place in `A` (src must be A).
-//   otherwise Bluestein: src may be A itself or another buffer; the result lands in A[0..r) and
-//   A[r..M) is clobbered.  Caller synchronised before; result visible to all threads on return.
+//   otherwise Bluestein: src may be A itself or another buffer; A[r..M) is clobbered.  The result goes to
+//   store(j, U[j]) when a store functor is given (leg2map: straight to the pixels), else to A[0..r).
+//   Caller synchronised before; with the default store the result is visible to all threads on return.
+struct StoreToA {
+  double2* A;
+  __device__ __forceinline__ void operator()(int k, double2 v) const { A[k] = v; }
+};
+template <class Store>
 __device__ void idft_r(double2* A, const double2* src, int r, int M, const double2* __restrict__ hhat,
-                       const Roots& W, const Tw& tw, int tid, int nt) {
-  if (M == 0) {  // r is a power of two
-    fft_dif<true>(A, r, tw, tid, nt);
-    bitrev_permute(A, r, tid, nt);
-    return;
-  }
+                       const Roots& W, const Tw& tw, int tid, int nt, const Store& store) {
   const int two_r = 2 * r;
-  // The work array is kept in the swizzled layout (swz<true>) between the chirp multiply and the final
-  // one.  Both boundary loops may run in place (src == A, result in A[0..r)): the swizzle permutes inside
-  // aligned groups of 8 elements, which one warp handles in one iteration, so "all lanes read, __syncwarp,
-  // all lanes write" is enough; the loops are uniform (every thread runs every iteration).
+  // The work array is kept in a swizzled layout between the chirp multiply and the final one (swz<3> with the
+  // radix-16 passes for M >= 256, swz<1> with the radix-4 passes below that).  Both boundary loops may run in place
+  // (src == A, result in A[0..r)): either swizzle permutes inside aligned groups of 8 elements, which one warp
+  // handles in one iteration, so "all lanes read, __syncwarp, all lanes write" is enough; the loops are uniform
+  // (every thread runs every iteration).
   // chirp c[k] = exp(i pi k^2 / r) = W(2 (k^2 mod 2r))
-  for (int kb = 0; kb < M; kb += nt) {
+  const bool big = M >= 256;
+  // M >= 2r: the upper half of the zero-padded input is empty, so the leading radix-2 DIF stage (odd log2 M) is
+  // lo[i] = a[i], hi[i] = a[i] w_M^i -- written here together with the chirp multiply instead of in a pass of its own
+  const bool lead2 = big && ((31 - __clz(M)) & 1);
+  const int h = M >> 1;
+  for (int kb = 0; kb < (lead2 ? h : M); kb += nt) {
     const int k = kb + tid;
     double2 v = make_double2(0.0, 0.0);
     if (k < r) {
@@ -278,27 +478,55 @@ __device__ void idft_r(double2* A, const double2* src, int r, int M, const doubl
       v = cmul(src[k], W(2 * q));
     }
     __syncwarp();
-    if (k < M) A[swz<true>(k)] = v;
+    if (lead2) {
+      if (k < h) {
+        A[swz<3>(k)] = v;
+        A[swz<3>(k + h)] = k < r ? cmul(v, tw.get<false>(k * (tw.T / M))) : v;
+      }
+    } else if (k < M) {
+      A[big ? swz<3>(k) : swz<1>(k)] = v;
+    }
   }
   __syncthreads();
-  fft_dif<false, true>(A, M, tw, tid, nt);
-  for (int k = tid; k < M; k += nt) {
-    const int p = swz<true>(k);
-    A[p] = cmul(A[p], __ldg(&hhat[k]));
+  if (big) {
+    fft_dif16<false>(A, M, tw, tid, nt, lead2);
+    // (multiplying the chirp spectrum in on the way into the first radix-16 DIT pass was measured slower: that pass
+    // gives every thread 16 consecutive elements, i.e. global loads 256 B apart across a warp)
+    for (int k = tid; k < M; k += nt) {
+      const int p = swz<3>(k);
+      A[p] = cmul(A[p], __ldg(&hhat[k]));
+    }
+    __syncthreads();
+    fft_dit16<true>(A, M, tw, tid, nt);
+  } else {
+    fft_dif<false, 1>(A, M, tw, tid, nt);
+    for (int k = tid; k < M; k += nt) {
+      const int p = swz<1>(k);
+      A[p] = cmul(A[p], __ldg(&hhat[k]));
+    }
+    __syncthreads();
+    fft_dit<true, 1>(A, M, tw, tid, nt);
   }
-  __syncthreads();
-  fft_dit<true, true>(A, M, tw, tid, nt);
   for (int kb = 0; kb < r; kb += nt) {
     const int k = kb + tid;
     double2 v = make_double2(0.0, 0.0);
     if (k < r) {
       const int q = (int)(((unsigned)k * (unsigned)k) % (unsigned)two_r);
-      v = cmul(A[swz<true>(k)], W(2 * q));
+      v = cmul(A[big ? swz<3>(k) : swz<1>(k)], W(2 * q));
     }
     __syncwarp();
-    if (k < r) A[k] = v;
+    if (k < r) store(k, v);
   }
   __syncthreads();
+}
+__device__ void idft_r(double2* A, const double2* src, int r, int M, const double2* __restrict__ hhat,
+                       const Roots& W, const Tw& tw, int tid, int nt) {
+  if (M == 0) {  // r is a power of two
+    fft_dif<true>(A, r, tw, tid, nt);
+    bitrev_permute(A, r, tid, nt);
+    return;
+  }
+  idft_r(A, src, r, M, hhat, W, tw, tid, nt, StoreToA{A});
 }
 
 // Shared-memory carve-up of one CTA.
@@ -343,7 +571,7 @@ size_t smem_bytes(int rmax, int Mmax, int nt) {
 // ------------------------------------------------------------------------------------------------
 // leg2map
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ desc, int first, const double2* __restrict__ leg,
+__global__ void __launch_bounds__(512) k_leg2map(const RingDesc* __restrict__ desc, int first, const double2* __restrict__ leg,
                           double* __restrict__ map, int64_t map_cstride, int64_t nm, int64_t nring,
                           const double2* __restrict__ hhat_all,
                           int rmax, int Mmax) {
@@ -464,17 +692,18 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
     for (int k = tid; k < r; k += nt) S.B[k] = S.A[k + r];
     __syncthreads();
     for (int half = 0; half < 2; ++half) {
-      idft_r(S.A, half == 0 ? S.A : S.B, r, d.M, hhat, W, TW, tid, nt);
-      FFT_PROF(3);
+      // the final chirp multiply writes the pixels directly
       if (al16) {
         double2* out2 = reinterpret_cast<double2*>(out);
-        for (int j = tid; j < r; j += nt) out2[2 * j + half] = S.A[j];
+        idft_r(S.A, half == 0 ? S.A : S.B, r, d.M, hhat, W, TW, tid, nt,
+               [=](int j, double2 v) { out2[2 * j + half] = v; });
       } else {
-        for (int j = tid; j < r; j += nt) {
-          out[4 * j + 2 * half] = S.A[j].x;
-          out[4 * j + 2 * half + 1] = S.A[j].y;
-        }
+        idft_r(S.A, half == 0 ? S.A : S.B, r, d.M, hhat, W, TW, tid, nt, [=](int j, double2 v) {
+          out[4 * j + 2 * half] = v.x;
+          out[4 * j + 2 * half + 1] = v.y;
+        });
       }
+      FFT_PROF(3);
       __syncthreads();  // A is reused as the work array of the second half
       FFT_PROF(4);
     }
@@ -484,7 +713,7 @@ __global__ void __launch_bounds__(1024) k_leg2map(const RingDesc* __restrict__ d
 // ------------------------------------------------------------------------------------------------
 // map2leg
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_map2leg(const RingDesc* __restrict__ desc, int first, const double* __restrict__ map,
+__global__ void __launch_bounds__(512) k_map2leg(const RingDesc* __restrict__ desc, int first, const double* __restrict__ map,
                           int64_t map_cstride, double2* __restrict__ leg, int64_t nm, int64_t nring,
                           const double2* __restrict__ hhat_all,
                           int rmax, int Mmax) {
@@ -893,6 +1122,190 @@ __global__ void __launch_bounds__(1024) k_build_hhat_long(const int* __restrict_
   }
 }
 
+// ================================================================================================
+// power-of-two rings (the whole equatorial belt of a power-of-two nside): one CTA per HALF ring
+//   leg2map:  u or v evaluated straight from the leg row in global memory (fold -> Zc -> u|v, no shared-memory
+//             passes), one r-point transform, 16-byte pixel stores.  A half ring of r = 4096 needs 64 KB, so
+//             three CTAs share an SM and the load / transform / store phases of different rings overlap
+//             (with one CTA per ring and SM they ran one after the other: profiles/r02_ringfft_phases.md).
+//   map2leg:  the two halves of a ring form a thread-block cluster; each transforms its half, then reads the
+//             other half's spectrum through distributed shared memory and writes its half of the leg row.
+// ================================================================================================
+struct HalfSmem {
+  double2* A;    // rmax
+  double2* hi;   // n-th roots: rmax*4/64 + 2
+  double2* lo;   // 64
+  double2* hi2;  // r-th roots: rmax/64 + 2
+  double2* lo2;  // 64
+};
+__device__ __forceinline__ HalfSmem carve_half(unsigned char* base, int rmax) {
+  HalfSmem s;
+  double2* p = reinterpret_cast<double2*>(base);
+  s.A = p;
+  p += rmax;
+  s.hi = p;
+  p += (rmax * 4) / 64 + 2;
+  s.lo = p;
+  p += 64;
+  s.hi2 = p;
+  p += rmax / 64 + 2;
+  s.lo2 = p;
+  return s;
+}
+size_t half_smem_bytes(int rmax) { return sizeof(double2) * ((size_t)rmax + (rmax * 4) / 64 + 2 + 64 + rmax / 64 + 2 + 64); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
+    k_leg2map_half(const RingDesc* __restrict__ desc, int first, const double2* __restrict__ leg, double* __restrict__ map,
+                   int64_t map_cstride, int64_t nm, int64_t nring, int rmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const RingDesc d = desc[first + (blockIdx.x >> 1)];
+  const int half = blockIdx.x & 1;  // == rank in the cluster: 0 transforms u, 1 transforms v
+  const int comp = blockIdx.y;
+  const HalfSmem S = carve_half(smem_raw, rmax);
+  const int n = d.nphi, r = d.r;
+  const int mmax = (int)nm - 1;
+  const double2* row = leg + ((int64_t)comp * nring + d.ir) * nm;
+  const Roots W{S.hi, S.lo};
+  const Tw TW{S.hi2, S.lo2, r};
+  FFT_PROF_INIT_C(3);
+  build_roots(S.hi, S.lo, n, 1.0, tid, nt);
+  build_roots(S.hi2, S.lo2, r, -1.0, tid, nt);
+  cluster.sync();  // tables built; the partner's shared memory exists
+  const Phase PH(d, W);
+  const int lgr = 31 - __clz(r);
+  FFT_PROF(0);
+  // front end shared by the two CTAs: each evaluates Zc[k], Zc[k + r] for half of the k's and hands u[k] to the
+  // u-CTA and v[k] to the v-CTA (one of the two stores goes through distributed shared memory)
+  double2* Au = half == 0 ? S.A : cluster.map_shared_rank(S.A, 0);
+  double2* Av = half == 1 ? S.A : cluster.map_shared_rank(S.A, 1);
+  const int kh = (r + 1) / 2;
+  const int k_lo = half == 0 ? 0 : kh, k_hi = half == 0 ? min(kh, r) : r;
+  if (mmax < 2 * r) {
+    // no aliasing (lmax < n / 2, e.g. the belt at lmax <= 2 nside - 1): X[j] = leg[j] exp(i j phi0) for j <= mmax, else 0.
+    // Four independent, coalesced loads per k (ascending and descending runs of the row) -- the generic fold below
+    // walks its alias loops one dependent load at a time.
+    const int N = 2 * r;
+    auto X = [&](int j) -> double2 {
+      if (j > mmax) return make_double2(0.0, 0.0);
+      const double2 v = __ldg(&row[j]);
+      return j == 0 ? make_double2(v.x, 0.0) : cmul(v, PH(j));
+    };
+#pragma unroll 4
+    for (int k = k_lo + tid; k < k_hi; k += nt) {
+      double2 a, b;
+      if (k == 0) {
+        const double x0 = X(0).x, xn = X(N).x;
+        const double2 xr = X(r);
+        a = make_double2(x0 + xn, x0 - xn);
+        b = make_double2(2.0 * xr.x, -2.0 * xr.y);
+      } else {
+        const double2 A1 = X(k), B1 = cconj(X(N - k)), A2 = X(k + r), B2 = cconj(X(r - k));
+        const double2 D1 = cmul(csub(A1, B1), W(k)), D2 = cmul(csub(A2, B2), W(k + r));
+        a = make_double2(A1.x + B1.x - D1.y, A1.y + B1.y + D1.x);  // P + i w^k (A - B)
+        b = make_double2(A2.x + B2.x - D2.y, A2.y + B2.y + D2.x);
+      }
+      Au[swz<2>(k, lgr)] = cadd(a, b);
+      Av[swz<2>(k, lgr)] = cmul(csub(a, b), W(2 * k));
+    }
+  } else {
+    for (int k = k_lo + tid; k < k_hi; k += nt) {
+      const double2 a = zc_eval(row, k, r, n, mmax, PH, W);
+      const double2 b = zc_eval(row, k + r, r, n, mmax, PH, W);
+      Au[swz<2>(k, lgr)] = cadd(a, b);
+      Av[swz<2>(k, lgr)] = cmul(csub(a, b), W(2 * k));
+    }
+  }
+  cluster.sync();
+  FFT_PROF(1);
+  fft_dif<true, 2>(S.A, r, TW, tid, nt);  // bit-reversed order: read back through the reversed index
+  FFT_PROF(3);
+  double* out = map + (int64_t)comp * map_cstride + d.pixoff;  // x[4j + 2 half], x[4j + 2 half + 1] = Re, Im
+  if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    double2* out2 = reinterpret_cast<double2*>(out);
+    for (int j = tid; j < r; j += nt) out2[2 * j + half] = S.A[swz<2>(brev_idx(j, lgr), lgr)];
+  } else {
+    for (int j = tid; j < r; j += nt) {
+      const double2 v = S.A[swz<2>(brev_idx(j, lgr), lgr)];
+      out[4 * j + 2 * half] = v.x;
+      out[4 * j + 2 * half + 1] = v.y;
+    }
+  }
+  FFT_PROF(4);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
+    k_map2leg_half(const RingDesc* __restrict__ desc, int first, const double* __restrict__ map, int64_t map_cstride,
+                   double2* __restrict__ leg, int64_t nm, int64_t nring, int rmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const RingDesc d = desc[first + (blockIdx.x >> 1)];
+  const int half = blockIdx.x & 1;  // == rank in the cluster
+  const int comp = blockIdx.y;
+  const HalfSmem S = carve_half(smem_raw, rmax);
+  const int n = d.nphi, r = d.r, N = 2 * r;
+  const int mmax = (int)nm - 1;
+  double2* row = leg + ((int64_t)comp * nring + d.ir) * nm;
+  const Roots W{S.hi, S.lo};
+  const Tw TW{S.hi2, S.lo2, r};
+  FFT_PROF_INIT_C(3);
+  build_roots(S.hi, S.lo, n, 1.0, tid, nt);
+  build_roots(S.hi2, S.lo2, r, -1.0, tid, nt);
+  FFT_PROF(8);
+  // pixels -> conj(u) (half 0) or conj(v) (half 1), stored bit-reversed so that the DIT delivers natural order
+  const double* in = map + (int64_t)comp * map_cstride + d.pixoff;
+  const int lgr = 31 - __clz(r);
+  if ((reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    const double2* in2 = reinterpret_cast<const double2*>(in);
+    for (int j = tid; j < r; j += nt) {
+      const double2 v = in2[2 * j + half];
+      S.A[swz<2>(brev_idx(j, lgr), lgr)] = make_double2(v.x, -v.y);
+    }
+  } else {
+    for (int j = tid; j < r; j += nt)
+      S.A[swz<2>(brev_idx(j, lgr), lgr)] = make_double2(in[4 * j + 2 * half], -in[4 * j + 2 * half + 1]);
+  }
+  __syncthreads();
+  FFT_PROF(9);
+  fft_dit<true, 2>(S.A, r, TW, tid, nt);  // conj(Uhat) or conj(Vhat)
+  cluster.sync();
+  FFT_PROF(10);
+  const double2* mine = S.A;
+  const double2* other = cluster.map_shared_rank(S.A, half ^ 1);
+  const double2* cu = half == 0 ? mine : other;   // conj(Uhat)
+  const double2* cv = half == 0 ? other : mine;   // conj(Vhat)
+  const Phase PH(d, W);
+  auto Z = [&](int k) -> double2 {  // k in [0, N]; Z[N] = Z[0]
+    if (k >= N) k -= N;
+    const int kk = k < r ? k : k - r;
+    const int ks = swz<2>(kk, lgr);
+    const double2 t = cmulc(cconj(cv[ks]), W(2 * kk));  // conj(w)^{2kk} Vhat
+    const double2 u = cconj(cu[ks]);
+    return k < r ? cadd(u, t) : csub(u, t);
+  };
+  // this CTA's half of the leg row: leg[m] = exp(-i m phi0) Xt[m mod n]
+  const int mh = (mmax + 2) / 2;
+  const int m_lo = half == 0 ? 0 : mh, m_hi = half == 0 ? min(mh, mmax + 1) : mmax + 1;
+  for (int m = m_lo + tid; m < m_hi; m += nt) {
+    const int km = m % n;
+    const bool up = km > N;
+    const int k = up ? n - km : km;
+    const double2 A = Z(k), B = cconj(Z(N - k));
+    const double2 Pp = make_double2(0.5 * (A.x + B.x), 0.5 * (A.y + B.y));
+    const double2 D = cmulc(csub(A, B), W(k == N ? 0 : k));
+    const double sg = (k == N) ? -1.0 : 1.0;  // conj(w)^N = -1
+    const double2 X = make_double2(Pp.x + sg * 0.5 * D.y, Pp.y - sg * 0.5 * D.x);  // P - i/2 conj(w^k)(A-B)
+    const double2 v = up ? cconj(X) : X;
+    row[m] = cmulc(v, PH(m));
+  }
+  cluster.sync();  // the partner may still be reading this CTA's shared memory
+  FFT_PROF(11);
+}
+
 int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -911,7 +1324,8 @@ static void raise_smem_attr(const void* fn, size_t* cur_by_dev, size_t want) {
   HP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
   *cur = want;
 }
-static size_t g_smem_leg2map[64] = {0}, g_smem_map2leg[64] = {0}, g_smem_hhat[64] = {0};
+static size_t g_smem_leg2map[64] = {0}, g_smem_map2leg[64] = {0}, g_smem_hhat[64] = {0}, g_smem_leg2map_half[64] = {0},
+              g_smem_map2leg_half[64] = {0};
 
 void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, const int64_t* ringstart,
                     int64_t nm, cudaStream_t stream, int64_t slot0, int64_t leg_nring) {
@@ -1009,6 +1423,7 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     const int b = work > 4096 ? 4 : (work > 2048 ? 3 : (work > 512 ? 2 : (work > 64 ? 1 : 0)));
     return (d.M ? 8 : 0) + b;
   };
+  const bool use_half = !getenv("HPSHT_FFT_NO_HALF");
   for (size_t i = 0; i < desc_.size();) {
     size_t j = i;
     Class c;
@@ -1021,13 +1436,16 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     }
     c.count = (int)(j - i);
     const int work = std::max(c.Mmax, c.rmax);
-    const char* ev = getenv("HPSHT_FFT_THREADS_BIG");
-    const int big = ev ? atoi(ev) : 1024;
-    c.threads = work > 2048 ? big : (work > 512 ? 256 : (work > 64 ? 128 : 64));
-    // 64 registers x 1024 threads fill an SM's register file: a class whose shared memory would let two CTAs
-    // share an SM gets 512 threads so that they actually can (one loads while the other transforms)
-    if (c.threads == 1024 && smem_bytes(c.rmax, c.Mmax, 512) <= 113 * 1024) c.threads = 512;
+    // the radix-16 passes hold 16 complex values per thread (k_leg2map / k_map2leg are compiled for <= 512 threads,
+    // 128 registers); an 8192-point pass has 512 butterflies
+    c.threads = work > 4096 ? 512 : (work > 512 ? 256 : (work > 64 ? 128 : 64));
     c.smem = smem_bytes(c.rmax, c.Mmax, c.threads);
+    // power-of-two rings of some length: one CTA per half ring (k_leg2map_half / k_map2leg_half)
+    c.half = use_half && c.Mmax == 0 && c.rmax >= 1024;
+    if (c.half) {
+      c.threads = c.rmax >= 1024 ? 256 : 128;
+      c.smem = half_smem_bytes(c.rmax);
+    }
     classes_.push_back(c);
     i = j;
   }
@@ -1046,11 +1464,15 @@ void RingFFT::setup(int64_t nring, const int64_t* nphi, const double* phi0, cons
     HP_CUDA(cudaFuncSetAttribute(k_build_hhat_long, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)long_smem_bytes(true)));
   }
-  size_t max_smem = 0;
-  for (auto& c : classes_) max_smem = std::max(max_smem, c.smem);
+  size_t max_smem = 0, max_half = 0;
+  for (auto& c : classes_) (c.half ? max_half : max_smem) = std::max(c.half ? max_half : max_smem, c.smem);
   HP_REQUIRE(max_smem <= 227 * 1024, HPSHT_ERR_UNSUPPORTED, "ring too long for the in-smem FFT");
   raise_smem_attr((const void*)k_leg2map, g_smem_leg2map, max_smem);
   raise_smem_attr((const void*)k_map2leg, g_smem_map2leg, max_smem);
+  if (max_half) {
+    raise_smem_attr((const void*)k_leg2map_half, g_smem_leg2map_half, max_half);
+    raise_smem_attr((const void*)k_map2leg_half, g_smem_map2leg_half, max_half);
+  }
   // chirp spectra
   d_hhat_.alloc((size_t)std::max<int64_t>(htotal, 1) * 2);
   if (!rs.empty()) {
@@ -1095,6 +1517,12 @@ void RingFFT::ensure_long_scratch(int ncomp) {
 void RingFFT::leg2map(const double* d_leg, double* d_map, int64_t map_cstride, int ncomp,
                       cudaStream_t stream) {
   for (const Class& c : classes_) {
+    if (c.half) {
+      k_leg2map_half<<<dim3(2u * (unsigned)c.count, (unsigned)ncomp), c.threads, c.smem, stream>>>(
+          d_desc_.p, c.first, reinterpret_cast<const double2*>(d_leg), d_map, map_cstride, nm_, nring_, c.rmax);
+      ++launches_;
+      continue;
+    }
     dim3 grid((unsigned)c.count, (unsigned)ncomp);
     k_leg2map<<<grid, c.threads, c.smem, stream>>>(
         d_desc_.p, c.first, reinterpret_cast<const double2*>(d_leg), d_map, map_cstride, nm_, nring_,
@@ -1120,6 +1548,12 @@ void RingFFT::leg2map(const double* d_leg, double* d_map, int64_t map_cstride, i
 void RingFFT::map2leg(const double* d_map, int64_t map_cstride, double* d_leg, int ncomp,
                       cudaStream_t stream) {
   for (const Class& c : classes_) {
+    if (c.half) {
+      k_map2leg_half<<<dim3(2u * (unsigned)c.count, (unsigned)ncomp), c.threads, c.smem, stream>>>(
+          d_desc_.p, c.first, d_map, map_cstride, reinterpret_cast<double2*>(d_leg), nm_, nring_, c.rmax);
+      ++launches_;
+      continue;
+    }
     dim3 grid((unsigned)c.count, (unsigned)ncomp);
     k_map2leg<<<grid, c.threads, c.smem, stream>>>(
         d_desc_.p, c.first, d_map, map_cstride, reinterpret_cast<double2*>(d_leg), nm_, nring_,

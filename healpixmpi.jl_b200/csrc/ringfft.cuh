@@ -56,6 +56,7 @@ class RingFFT {
     int threads = 0;
     size_t smem = 0;
     int rmax = 0, Mmax = 0;
+    bool half = false;         // power-of-two rings: one CTA per half ring
   };
   int64_t nring_ = 0, nrings_own_ = 0, nm_ = 0, npix_ = 0;
   int64_t launches_ = 0;

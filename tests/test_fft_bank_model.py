@@ -27,3 +27,12 @@ def test_swizzle_is_conflict_free_and_local():
     s = idx ^ ((idx >> 2) & 7)
     assert np.array_equal(np.sort(s), idx)
     assert np.all((s >> 3) == (idx >> 3))  # a permutation inside every aligned group of 8
+
+
+def test_round2_layouts_are_conflict_free():
+    """swz2 (half-ring kernels of the power-of-two rings: contiguous, descending, bit-reversed and radix-4 accesses;
+    the plain layout is 8-way conflicted on the bit-reversed one) and swz3 (radix-16 passes of the Bluestein array)."""
+    assert model.check_round2_layouts()
+    for M, lg in ((1024, 10), (4096, 12)):
+        idx = np.arange(M)
+        assert np.all((model.swz2(idx, lg) >> 3) == (idx >> 3)) and np.all((model.swz3(idx) >> 3) == (idx >> 3))

@@ -16,7 +16,16 @@ L.hpsht_debug_fft_profile(buf, 1)
 plan.alm2map(a, m, 1)
 L.hpsht_debug_fft_profile(buf, 0)
 names = ["root tables", "fold", "X->Zc->u|v", "FFT / Bluestein", "pixel store"]
-for c, cn in enumerate(["power-of-two rings", "Bluestein M = 8192", "Bluestein M <= 4096"]):
+for c, cn in enumerate(["power-of-two rings", "Bluestein M = 8192", "Bluestein M <= 4096", "power-of-two rings, half-ring CTAs"]):
     v = np.array(buf[c * 16:c * 16 + 5], dtype=float)
+    if v.sum() == 0:
+        continue
     print(cn, "total Mcycles %.1f:" % (v.sum() / 1e6), ", ".join(f"{n} {100 * x / v.sum():.0f}%" for n, x in zip(names, v)))
 print("ring fft stage ms", plan.timings()["ringfft"])
+L.hpsht_debug_fft_profile(buf, 1)
+plan.adjoint_alm2map(m, a, 1)
+L.hpsht_debug_fft_profile(buf, 0)
+v = np.array(buf[3 * 16 + 8:3 * 16 + 12], dtype=float)
+if v.sum() > 0:
+    print("map2leg half-ring CTAs total Mcycles %.1f:" % (v.sum() / 1e6), ", ".join(f"{n} {100 * x / v.sum():.0f}%" for n, x in zip(["root tables", "pixel load", "FFT", "Z / X / un-alias / leg store"], v)))
+print("ring fft stage ms (adjoint)", plan.timings()["ringfft"])

@@ -54,7 +54,65 @@ def fft_cost(M, swz):
     return total, ideal
 
 
+def swz2(i, lg):
+    """half-ring kernels of the power-of-two rings: low three bits ^ bits 2..4 ^ the top three bits"""
+    return i ^ (((i >> 2) ^ (i >> (lg - 3))) & 7)
+
+
+def swz3(i):
+    """Bluestein work array with the radix-16 passes: low three bits ^ bits 4..6"""
+    return i ^ ((i >> 4) & 7)
+
+
+def plain_wavefronts(idx):
+    w, n = wavefronts(idx, False)
+    return w, n
+
+
+def check_round2_layouts():
+    """(1) swz2: contiguous, descending, bit-reversed and every radix-4 pass conflict free for M = 1024 .. 4096;
+    (2) swz3: contiguous accesses and every element column of every radix-16 pass conflict free."""
+    for M in (1024, 2048, 4096):
+        lg = int(np.log2(M))
+        i = np.arange(M)
+        assert np.array_equal(np.sort(swz2(i, lg)), i)
+        br = np.array([int(format(x, f"0{lg}b")[::-1], 2) for x in i])
+        for pat in (i, i[::-1].copy(), br):
+            w, n = plain_wavefronts(swz2(pat, lg))
+            assert w == n, (M, w, n)
+        w, n = plain_wavefronts(br)
+        assert w == 8 * n  # the plain layout: 8-way conflicts on the bit-reversed access
+        L = M // 2 if lg & 1 else M
+        while L >= 4:
+            q = L // 4
+            loads, _ = pass_indices(M, q, 256)
+            for idx in loads:
+                w, n = plain_wavefronts(swz2(idx, lg))
+                assert w == n, (M, q, w, n)
+            L //= 4
+    for M in (256, 4096, 8192):
+        i = np.arange(M)
+        assert np.array_equal(np.sort(swz3(i)), i)
+        w, n = plain_wavefronts(swz3(i))
+        assert w == n
+        L = M
+        while (int(np.log2(L)) & 3) != 0:
+            L //= 2
+        while L >= 16:
+            q, q1 = L // 4, L // 16
+            t = np.arange(M // 16)
+            base = (t >> int(np.log2(q1))) * L + (t & (q1 - 1))
+            for a in range(4):
+                for c in range(4):
+                    w, n = plain_wavefronts(swz3(base + a * q + c * q1))
+                    assert w == n, (M, L, a, c, w, n)
+            L //= 16
+    return True
+
+
 if __name__ == "__main__":
+    check_round2_layouts()
+    print("round-2 layouts: swz2 (half-ring kernels) and swz3 (radix-16 Bluestein) conflict free")
     for M in (4096, 8192):
         for swz in (False, True):
             t, i = fft_cost(M, swz)
