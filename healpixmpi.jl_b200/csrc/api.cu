@@ -281,7 +281,7 @@ void hpsht_plan::ensure_stages() {
 namespace {
 int wanted_ring_blocks(int64_t nside, int P) {
   const char* eb = getenv("HPSHT_HOST_BLOCKS");
-  int want = eb ? std::max(1, atoi(eb)) : (P <= 2 ? 7 : 5);
+  int want = eb ? std::max(1, atoi(eb)) : (P <= 2 ? 9 : 5);
   if (!eb && 12 * nside * nside / P < (1 << 22)) want = 1;  // small maps: the copies are microseconds
   return want;
 }

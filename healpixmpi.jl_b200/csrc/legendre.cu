@@ -1281,7 +1281,6 @@ int64_t max_of(const std::vector<int64_t>& v) {
   for (int64_t x : v) m = std::max(m, x);
   return m;
 }
-int64_t gcd_i(int64_t a, int64_t b) { return b == 0 ? a : gcd_i(b, a % b); }
 }  // namespace
 
 void LegendreStage::setup(int64_t lmax, const int64_t* mval, const int64_t* mstart, int64_t nm,
@@ -1373,13 +1372,14 @@ std::vector<int> cut_ring_blocks(const std::vector<PairHost>& pairs, int want, c
   const int np = (int)pairs.size();
   if (want < 1) want = 1;
   bp.push_back(0);
-  // Preferred cut: multiples of the least common multiple of the kernels' tile sizes (512 pairs), so that
-  // no block ends in a partly filled tile and no accuracy class is cut inside a tile.  Block sizes grow from
-  // both ends towards the middle (1, 2, 3, ... units): what a pipelined call cannot hide is the polar block's
-  // share of the alm copy and the equator-most block's map copy, and a block's copy must fit behind the
-  // compute of its (smaller) neighbour towards the end (nside 4096, want 7: 512 1024 1536 2048 1536 1024 512).
-  int64_t align = 32;
-  for (int t : {syn_tile(0, LK_STD), syn_tile(2, LK_STD), adj_tile(0), adj_tile(2)}) align = align / gcd_i(align, t) * t;
+  // Preferred cut: multiples of 256 pairs -- the tile of every kernel but the spin-0 synthesis (512), whose tiles
+  // then end half filled at some block boundaries -- and never inside an accuracy class's tile (the class ranges
+  // are multiples of 256 too).  Block sizes grow from both ends towards the middle (1, 2, 3, ... units): what a
+  // pipelined call cannot hide is the polar block's share of the alm copy and the equator-most block's map copy,
+  // and a block's copy must fit behind the compute of its (smaller) neighbour towards the end (nside 4096, want 9:
+  // 256 512 768 1024 3072 1024 768 512 256; measured against units of 512 and 128 pairs in profiles/r02_e2e.md).
+  int64_t align = 256;
+  if (const char* eu = getenv("HPSHT_BLOCK_UNIT")) align = std::max(32, atoi(eu));
   if (want > 1 && np >= 2 * align) {
     const int64_t units = (np + align - 1) / align;  // last unit may be partial
     std::vector<int64_t> left, right;
