@@ -558,9 +558,11 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp, b
       }
       alm_done_from = lo;
     };
-    // the small equator-most blocks go first so that the compute starts early
-    for (int b = NB - 1; b >= 0; --b) {
-      if (!in_dev) {
+    // the small equator-most blocks go first so that the compute starts early.  All input copies are queued before
+    // anything else: with one copy stream (P > 1) an alm piece going out between two of them would otherwise hold
+    // the next block's pixels back until the Legendre kernels of the current block are done.
+    if (!in_dev)
+      for (int b = NB - 1; b >= 0; --b) {
         if (phi(b) > plo(b))
           for (int c = 0; c < ncomp; ++c) {
             const size_t o = (size_t)c * npix_loc + (size_t)plo(b);
@@ -569,6 +571,7 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp, b
           }
         HP_CUDA(cudaEventRecord(ev_blk[(size_t)b], hstream));
       }
+    for (int b = NB - 1; b >= 0; --b) {
       const int64_t j0 = blo(set, b, rank), nj = bhi(set, b, rank) - j0;
       if (P == 1) {
         if (!in_dev) HP_CUDA(cudaStreamWaitEvent(stream, ev_blk[(size_t)b], 0));
