@@ -253,10 +253,11 @@ void hpsht_plan::ensure_stages() {
   }
   HP_CUDA(cudaStreamCreateWithPriority(&fstream, cudaStreamNonBlocking, prio_hi));
   HP_CUDA(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
-  // Several ranks of one host share its memory system: on the 8 x B200 box a rank's H2D runs at 21.5 GB/s alone but
-  // at 7.4 GB/s per direction when its D2H runs too (tools/h2d_bench.py, profiles/r02_multi_gpu.md) -- P > 1 keeps
-  // one copy stream so that the two directions take turns; a single rank gets one stream per direction.
-  if (P == 1) HP_CUDA(cudaStreamCreateWithFlags(&ostream, cudaStreamNonBlocking));
+  // Several ranks of one host share its memory system (tools/h2d_bench.py on the 8 x B200 box, GB/s per rank, H2D
+  // alone vs H2D and D2H at once per direction: 2 ranks 51.7 vs 31.1, 4 ranks 35.5 vs 13.8, 8 ranks 21.5 vs 7.4;
+  // profiles/r02_multi_gpu.md): from 4 ranks on the two directions are faster taking turns on one copy stream,
+  // up to 2 ranks each direction gets its own.
+  if (P <= 2) HP_CUDA(cudaStreamCreateWithFlags(&ostream, cudaStreamNonBlocking));
   else ostream = hstream;
   for (cudaEvent_t* e : {&ev_hdone, &ev_a0, &ev_a1, &ev_entry, &ev_user, &ev_done})
     HP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
