@@ -253,12 +253,11 @@ void hpsht_plan::ensure_stages() {
   }
   HP_CUDA(cudaStreamCreateWithPriority(&fstream, cudaStreamNonBlocking, prio_hi));
   HP_CUDA(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
-  // Several ranks of one host share its memory system (tools/h2d_bench.py on the 8 x B200 box, GB/s per rank, H2D
-  // alone vs H2D and D2H at once per direction: 2 ranks 51.7 vs 31.1, 4 ranks 35.5 vs 13.8, 8 ranks 21.5 vs 7.4;
-  // profiles/r02_multi_gpu.md): from 4 ranks on the two directions are faster taking turns on one copy stream,
-  // up to 2 ranks each direction gets its own.
-  if (P <= 2) HP_CUDA(cudaStreamCreateWithFlags(&ostream, cudaStreamNonBlocking));
-  else ostream = hstream;
+  // One copy stream per direction.  (Several ranks of one host share its memory system -- tools/h2d_bench.py on the
+  // 8 x B200 box, GB/s per rank, H2D alone vs H2D and D2H at once per direction: 2 ranks 51.7 vs 31.1, 4 ranks 35.5 vs
+  // 13.8, 8 ranks 21.5 vs 7.4 -- but inside a transform the two directions rarely meet, and one shared stream made
+  // the 8-rank host-pointer step slower, 161.6 -> 178.7 ms: profiles/r02_multi_gpu.md.)
+  HP_CUDA(cudaStreamCreateWithFlags(&ostream, cudaStreamNonBlocking));
   for (cudaEvent_t* e : {&ev_hdone, &ev_a0, &ev_a1, &ev_entry, &ev_user, &ev_done})
     HP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   leg.setup(lmax, mval.data(), mstart.data(), nm_loc, nr_tot, thetatot.data(), lay, max_ncomp, stream);
