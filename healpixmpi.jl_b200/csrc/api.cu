@@ -279,9 +279,13 @@ void hpsht_plan::ensure_stages() {
 // [blo, bhi) of its local rings.  Everything that decides the cut is the same on every rank (the ranks of a
 // collective call must cut the same blocks): nside, lmax, P and the environment -- no rank-local quantity.
 namespace {
+// up to 2 ranks: blocks that grow from both ends (the copies are 0.3 - 0.6 of the compute, only the end blocks show);
+// from 4 ranks on the ranks share the host's memory system, a block's copy takes about as long as its compute, and
+// equal blocks pipeline best (profiles/r02_multi_gpu.md)
+bool equal_ring_blocks(int P) { return P >= 4; }
 int wanted_ring_blocks(int64_t nside, int P) {
   const char* eb = getenv("HPSHT_HOST_BLOCKS");
-  int want = eb ? std::max(1, atoi(eb)) : (P <= 2 ? 9 : 5);
+  int want = eb ? std::max(1, atoi(eb)) : (P <= 2 ? 9 : 8);
   if (!eb && 12 * nside * nside / P < (1 << 22)) want = 1;  // small maps: the copies are microseconds
   return want;
 }
@@ -328,12 +332,12 @@ void hpsht_plan::setup_blocks() {
     std::vector<int64_t> tot = rr_rindexes_tot(2 * nside, P);
     for (size_t i = 0; i < tot.size(); ++i) w[i] = (double)healpix_ring(nside, tot[i]).nphi;
   }
-  HB = leg.setup_blocks(wanted_ring_blocks(nside, P), w.data());
+  HB = leg.setup_blocks(wanted_ring_blocks(nside, P), w.data(), equal_ring_blocks(P));
   if (HB <= 1) return;
   std::vector<int> bp;
   // the pair list the Legendre stage cut is the one build_pairs gives for thetatot
   const std::vector<PairHost> pairs = build_pairs(lmax, nr_tot, thetatot.data());
-  bp = cut_ring_blocks(pairs, wanted_ring_blocks(nside, P), w.data());
+  bp = cut_ring_blocks(pairs, wanted_ring_blocks(nside, P), w.data(), equal_ring_blocks(P));
   if (!ring_block_ranges(pairs, bp, nr_of, bj_lo, bj_hi)) {  // exotic ring order: no blocking
     HB = leg.setup_blocks(1, w.data());
     return;
@@ -1119,7 +1123,7 @@ int hpsht_ring_block_ranges(int64_t nside, int64_t lmax, int n_ranks, int* nbloc
     }
     for (int t = 0; t < n_ranks; ++t) nr_of[(size_t)t] = rr_nrings(eq, t, n_ranks);
     const std::vector<PairHost> pairs = build_pairs(lmax, nr_tot, theta.data());
-    std::vector<int> bp = cut_ring_blocks(pairs, wanted_ring_blocks(nside, n_ranks), w.data());
+    std::vector<int> bp = cut_ring_blocks(pairs, wanted_ring_blocks(nside, n_ranks), w.data(), equal_ring_blocks(n_ranks));
     std::vector<int64_t> l, h;
     if (bp.size() <= 2 || !ring_block_ranges(pairs, bp, nr_of, l, h)) {
       bp = {0, (int)pairs.size()};

@@ -1367,7 +1367,7 @@ void LegendreStage::setup(int64_t lmax, const int64_t* mval, const int64_t* msta
 }
 
 // ---- ring blocks -----------------------------------------------------------------------------
-std::vector<int> cut_ring_blocks(const std::vector<PairHost>& pairs, int want, const double* slot_weight) {
+std::vector<int> cut_ring_blocks(const std::vector<PairHost>& pairs, int want, const double* slot_weight, bool equal) {
   std::vector<int> bp;
   const int np = (int)pairs.size();
   if (want < 1) want = 1;
@@ -1384,7 +1384,15 @@ std::vector<int> cut_ring_blocks(const std::vector<PairHost>& pairs, int want, c
     const int64_t units = (np + align - 1) / align;  // last unit may be partial
     std::vector<int64_t> left, right;
     int64_t rem = units;
-    for (int64_t k = 1; (int64_t)(left.size() + right.size()) + 3 <= want && rem >= 2 * k + 1; ++k) {
+    if (equal) {
+      // copy-bound callers (several ranks sharing one host's memory system: the copy of a block takes about as
+      // long as its compute) want every block's copy to fit behind the next block's compute: equal blocks
+      const int64_t nb = std::min<int64_t>(want, units);
+      for (int64_t b = 1; b < nb; ++b) left.push_back(units * b / nb - units * (b - 1) / nb);
+      left.push_back(units - units * (nb - 1) / nb);
+      rem = 0;
+    }
+    for (int64_t k = 1; !equal && (int64_t)(left.size() + right.size()) + 3 <= want && rem >= 2 * k + 1; ++k) {
       left.push_back(k);
       right.push_back(k);
       rem -= 2 * k;
@@ -1424,8 +1432,8 @@ std::vector<int> cut_ring_blocks(const std::vector<PairHost>& pairs, int want, c
   return bp;
 }
 
-int LegendreStage::setup_blocks(int want, const double* slot_weight) {
-  blk_pair_[1] = cut_ring_blocks(pairs_, want, slot_weight);
+int LegendreStage::setup_blocks(int want, const double* slot_weight, bool equal) {
+  blk_pair_[1] = cut_ring_blocks(pairs_, want, slot_weight, equal);
   have_[0] = have_[1] = false;
   return nblocks(1);
 }

@@ -62,7 +62,7 @@ class LegendreStage {
   // pipeline  Legendre(block) -> exchange(block) -> ring FFT(block) -> device-to-host copy(block)  and the
   // reverse for the adjoint.  Block set 0 always is the single block holding every pair; setup_blocks
   // builds set 1 and returns its number of blocks.  Call right after setup().
-  int setup_blocks(int want, const double* slot_weight);
+  int setup_blocks(int want, const double* slot_weight, bool equal = false);
   int nblocks(int set) const { return (int)blk_pair_[set].size() - 1; }
   std::vector<int64_t> block_slot_list(int set, int b) const;   // every ring slot of the block
   // number of local m's (a prefix) that block b touches at all
@@ -136,6 +136,7 @@ class LegendreStage {
 // Generic N/S pair detection on an arbitrary theta list (pole -> equator order).
 std::vector<PairHost> build_pairs(int64_t lmax, int64_t nring, const double* theta);
 // first pair of each ring block (+ the end): the pole -> equator pair list cut into <= want ranges (host only)
-std::vector<int> cut_ring_blocks(const std::vector<PairHost>& pairs, int want, const double* slot_weight);
+std::vector<int> cut_ring_blocks(const std::vector<PairHost>& pairs, int want, const double* slot_weight,
+                                 bool equal = false);
 
 }  // namespace hpsht
