@@ -402,7 +402,7 @@ void hpsht_plan::run(bool synthesis, const double* in, double* out, int ncomp, b
   HP_REQUIRE(in && out, HPSHT_ERR_ARG, "null data pointer");
   HP_CUDA(cudaSetDevice(device));
   ensure_stages();
-  if (times_pending) finish_times();
+  if (times_pending && !async) finish_times();  // (a stream-ordered call never blocks: it just supersedes them)
   leg.reset_launches();
   fft.reset_launches();
   int64_t extra = 0;

@@ -12,6 +12,7 @@ Julia's trailing ``!`` is spelled as a trailing underscore."""
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import weakref
 
 import numpy as np
@@ -210,8 +211,19 @@ class Plan:
 _PLANS: dict = {}
 
 
+def _geom_key(thetatot, phi0):
+    """The geometry a plan is built with is part of its identity: a DMap with another thetatot / phi0 must not
+    pick up a plan made for the standard HEALPix rings."""
+    if thetatot is None and phi0 is None:
+        return None
+    h = hashlib.blake2b(digest_size=16)
+    for a in (thetatot, phi0):
+        h.update(b"-" if a is None else np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    return h.hexdigest()
+
+
 def get_plan(nside: int, lmax: int, comm: Comm, thetatot=None, phi0=None) -> Plan:
-    key = (nside, lmax, comm)
+    key = (nside, lmax, comm, _geom_key(thetatot, phi0))
     p = _PLANS.get(key)
     if p is None:
         p = Plan(nside, lmax, comm, 2, -1, thetatot, phi0)
@@ -246,6 +258,14 @@ def _checks(d_alm: DAlm, d_map: DMap):
 
 
 def _check_plan_matches(plan: Plan, d_alm: DAlm, d_map: DMap) -> None:
+    """The C ABI takes raw pointers: everything it will assume about the two buffers is checked here
+    (descriptor arrays, element type, extent), so a mismatch raises instead of reading or writing out of bounds."""
+    for name, a, dt, n in (("DAlm.alm", d_alm.alm, np.complex128, plan.nalm_loc), ("DMap.pixels", d_map.pixels, np.float64, plan.npix_loc)):
+        if isinstance(a, np.ndarray) and (a.dtype != dt or a.shape[0] != n):
+            raise _lib.DomainError(_lib.HPSHT_ERR_ARG, f"{name} must be {np.dtype(dt).name} with {n} rows, got "
+                                                       f"{a.dtype.name} with {a.shape[0]}")
+    if d_alm.info.mmax != d_alm.info.lmax:
+        raise _lib.DomainError(_lib.HPSHT_ERR_ARG, "mmax must equal lmax (src/alm.jl:171)")
     mval, mstart0 = plan.alm_info()
     if not (np.array_equal(mval, d_alm.info.mval) and np.array_equal(mstart0 + 1, d_alm.info.mstart)):
         raise _lib.DomainError(_lib.HPSHT_ERR_ARG, "DAlm.info does not describe an RR shard of this communicator")

@@ -542,3 +542,60 @@ def test_config5_nside8192_adjointness(H, O):
     sc, sd = plan.legendre_steps(0)
     assert abs(sc / 1.7409e12 - 1) < 1e-3  # SURVEY 8d work model
     plan.destroy()
+
+
+def test_stream_ordered_calls_match_blocking_calls(H):
+    """hpsht_alm2map_async / hpsht_adjoint_alm2map_async (device pointers, ordered after the caller's stream, host not
+    blocked) give bit-identical results to the blocking forms, also when the input is produced on the caller's
+    stream right before the call and the output is consumed on it right after."""
+    import torch
+
+    nside, lmax = 256, 511
+    plan = H.Plan(nside, lmax, H.COMM_SELF, 2)
+    st = torch.cuda.Stream()
+    for ncomp in (1, 2):
+        g = torch.Generator(device="cuda").manual_seed(7 + ncomp)
+        a = torch.randn((ncomp, plan.nalm_loc, 2), dtype=torch.float64, device="cuda", generator=g)
+        f = torch.randn((ncomp, plan.npix_loc), dtype=torch.float64, device="cuda", generator=g)
+        m_ref, a_ref = torch.zeros_like(f), torch.zeros_like(a)
+        plan.alm2map(a, m_ref, ncomp)
+        plan.adjoint_alm2map(f, a_ref, ncomp)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(st):
+            a2 = a * 2.0                      # produced on the caller's stream
+            m_out = torch.zeros_like(f)
+            plan.alm2map_async(a2, m_out, ncomp, st.cuda_stream)
+            m_half = m_out * 0.5              # consumed on the caller's stream, no host sync in between
+            a_out = torch.zeros_like(a)
+            plan.adjoint_alm2map_async(f, a_out, ncomp, st.cuda_stream)
+            a_copy = a_out.clone()
+        st.synchronize()
+        plan.synchronize()
+        assert torch.equal(m_half, m_ref)     # linear in a: (Y 2a) / 2 == Y a exactly (powers of two)
+        assert torch.equal(a_copy, a_ref)
+        assert plan.timings()["total"] > 0
+    # host pointers are refused by the stream-ordered forms
+    with pytest.raises(H.DomainError):
+        plan.alm2map_async(np.zeros((1, plan.nalm_loc), dtype=np.complex128), np.zeros((1, plan.npix_loc)), 1, 0)
+    plan.destroy()
+
+
+def test_binding_rejects_mismatched_shards(H):
+    """The Python mirror checks extent and element type of the DAlm / DMap buffers against the plan before any raw
+    pointer reaches the C ABI."""
+    nside, lmax = 8, 15
+    d_alm, d_map = H.DAlm(), H.DMap()
+    H.Scatter_(H.Alm(lmax, lmax), d_alm)
+    H.Scatter_(H.HealpixMap(nside), d_map)
+    H.alm2map_(d_alm, d_map)
+    good = d_alm.alm
+    d_alm.alm = np.asfortranarray(good[:-1])
+    with pytest.raises(H.DomainError):
+        H.alm2map_(d_alm, d_map)
+    d_alm.alm = np.asfortranarray(good.astype(np.complex64))
+    with pytest.raises(H.DomainError):
+        H.alm2map_(d_alm, d_map)
+    d_alm.alm = good
+    d_map.pixels = np.asfortranarray(d_map.pixels[:-4])
+    with pytest.raises(H.DomainError):
+        H.adjoint_alm2map_(d_map, d_alm)
