@@ -93,6 +93,17 @@ def lam(spin: int, lmax: int, m: int, theta: float) -> np.ndarray:
     return out
 
 
+def lam_quad(spin: int, lmax: int, m: int, theta: float):
+    """The same recurrence in __float128, returned as (hi, lo) double arrays; None if the start value leaves the
+    quad range.  Only for checking lam() at large l (tests/test_oracle.py)."""
+    hi = np.zeros(lmax + 1)
+    lo = np.zeros(lmax + 1)
+    f = lib().orc_lambda_quad
+    f.restype = C.c_int
+    rc = f(C.c_int(spin), C.c_int64(lmax), C.c_int64(m), C.c_double(theta), _p(hi), _p(lo))
+    return None if rc else (hi, lo)
+
+
 def brute_sylm(s: int, l: int, m: int, theta: float) -> float:
     return lib().orc_brute_sylm(s, l, m, theta)
 

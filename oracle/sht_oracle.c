@@ -3,7 +3,7 @@
  * product path; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference
  * legs may use anything under oracle/).
  *
- * Extended-precision (x87 80-bit long double, __float128 for the brute-force part) CPU
+ * Extended-precision (x87 80-bit long double; __float128 for the brute-force part and the polar rings) CPU
  * restatement of the arithmetic that HealpixMPI.jl's hot path delegates to Ducc0:
  *     alm2leg! / leg2map! / map2leg! / leg2alm!        (reference src/sht.jl:85,93,169,178)
  * in the data layouts the reference passes across that seam (src/sht.jl:67-69,97-98,182-183).
@@ -21,7 +21,11 @@
  *   (2) a brute-force __float128 double sum over explicit sY_lm (orc_brute_synth) that shares
  *       no recurrence with the staged path;
  *   (3) analytic known answers (a00 = sqrt(4pi) -> map == 1; single-alm maps; E22 closed form);
- *   (4) scipy.special.sph_harm_y for spin 0;
+ *   (4) third-party implementations: scipy.special.sph_harm_y (double), mpmath.spherharm at 40 digits (spin 0,
+ *       agreement 5e-18), sympy's exact Wigner small-d for the spin-weighted functions and their sign convention
+ *       (agreement 2e-17) -- tests/test_oracle.py;
+ *   (4b) its own accuracy at l = 8191, measured against the same recurrences in __float128 (orc_lambda_quad):
+ *       <= 2e-14 everywhere, ~1e-18 on the rings next to the poles, which run in __float128 (see use_quad);
  *   (5) the adjointness identity <f, Y a> = <Y^T f, a>_w with the localdot weighting
  *       (src/alm.jl:634-644).
  * Algorithms here are deliberately DIFFERENT from the product's (plain three-term recurrences
@@ -37,8 +41,27 @@
 #include <string.h>
 
 typedef long double ld;
+typedef __float128 q128;
 
 #define ORC_PI 3.14159265358979323846264338327950288419716939937510L
+
+/* cos(theta) as an unevaluated sum hi + lo of two long doubles (lo from a __float128 evaluation).
+ * Why: the recurrences multiply the running value by x = cos(theta), and d(lambda)/dx ~ l / sin(theta), so the
+ * 2.7e-20 rounding of a plain long-double cosine is amplified to 1e-12 relative at l = 8191 on the innermost HEALPix
+ * rings (sin(theta) ~ 2e-4) -- the very accuracy this file is used to certify.  tests/test_oracle.py measured it
+ * against mpmath (6.7e-17 at l = 48, theta = 0.02) before this was added. */
+static void cos_hi_lo(ld th, ld* hi, ld* lo) {
+  __float128 c = cosq((__float128)th);
+  *hi = (ld)c;
+  *lo = (ld)(c - (__float128)*hi);
+}
+
+/* Near the poles even the compensated long-double recurrence is not good enough: rounding errors injected at every
+ * step grow like l^2 for l*theta < 1 (the second solution of the recurrence is singular at the pole), measured
+ * 5.6e-13 relative at l = 8191 on the first ring of nside 4096 against the __float128 recurrence, 1.4e-14 on the third
+ * ring, < 1e-15 from lmax*sin(theta) = 80 on.  Rings with lmax*sin(theta) < 32 (about 20 rings per pole at the
+ * headline size; they carry few m) therefore run the recurrence itself in __float128. */
+static int use_quad(ld th, int64_t lmax) { return fabsl(sinl(th)) * (ld)lmax < 64.0L; }
 
 /* ------------------------------------------------------------------------------------------
  * HEALPix RING-scheme geometry of ring `ring` (1-based, 1..4*nside-1).  Restates what
@@ -124,7 +147,8 @@ static const ld RESCALE_DOWN = 0x1p-8192L;
  * Recurrence: x*lam_l = eps_{l+1} lam_{l+1} + eps_l lam_{l-1}, eps_l = sqrt((l^2-m^2)/(4l^2-1)).
  * Values whose magnitude is below 2^-4096 are returned as 0. */
 static void lam_row_spin0(int64_t lmax, int64_t m, ld th, ld* out) {
-  ld x = cosl(th), sth = sinl(th);
+  ld x, xlo, sth = sinl(th);
+  cos_hi_lo(th, &x, &xlo);
   for (int64_t l = 0; l < m && l <= lmax; ++l) out[l] = 0.0L;
   if (m > lmax) return;
   /* lam_mm = (-1)^m sqrt((2m+1)/(4pi)) * sqrt(prod_{k=1..m} (2k-1)/(2k)) * sin^m */
@@ -152,12 +176,30 @@ static void lam_row_spin0(int64_t lmax, int64_t m, ld th, ld* out) {
   ld cur = ldexpl(st.v, (int)(st.e - SCALE_STEP * sc));
   ld prev = 0.0L;
   ld m2 = (ld)m * (ld)m;
+  if (use_quad(th, lmax)) { /* same recurrence, same range management, 113-bit arithmetic */
+    q128 qx = cosq((q128)th), qc = cur, qp = 0, qm2 = (q128)m * m;
+    for (int64_t l = m; l <= lmax; ++l) {
+      out[l] = (sc == 0) ? (ld)qc : 0.0L;
+      q128 fl = l, fl1 = l + 1;
+      q128 el = (l == m) ? 0 : sqrtq((fl * fl - qm2) / (4 * fl * fl - 1));
+      q128 el1 = sqrtq((fl1 * fl1 - qm2) / (4 * fl1 * fl1 - 1));
+      q128 nx = (qx * qc - el * qp) / el1;
+      qp = qc;
+      qc = nx;
+      if (fabsq(qc) > (q128)BIG && sc < 0) {
+        qc *= (q128)RESCALE_DOWN;
+        qp *= (q128)RESCALE_DOWN;
+        sc += 1;
+      }
+    }
+    return;
+  }
   for (int64_t l = m; l <= lmax; ++l) {
     out[l] = (sc == 0) ? cur : 0.0L;
     ld l1 = (ld)(l + 1);
     ld eps_l = (l == m) ? 0.0L : sqrtl(((ld)l * (ld)l - m2) / (4.0L * (ld)l * (ld)l - 1.0L));
     ld eps_l1 = sqrtl((l1 * l1 - m2) / (4.0L * l1 * l1 - 1.0L));
-    ld nxt = (x * cur - eps_l * prev) / eps_l1;
+    ld nxt = ((x * cur - eps_l * prev) + xlo * cur) / eps_l1;
     prev = cur;
     cur = nxt;
     if (fabsl(cur) > BIG && sc < 0) {
@@ -176,7 +218,8 @@ static void lam_row_spin0(int64_t lmax, int64_t m, ld th, ld* out) {
  *   C_l = sqrt((l^2-m^2)(l^2-s^2)/(l^2 (4l^2-1))).
  * Start at l0 = max(m,2) with the single-term closed forms of the sum. Requires m >= 0. */
 static void lam_row_spin2(int s, int64_t lmax, int64_t m, ld th, ld* out) {
-  ld x = cosl(th);
+  ld x, xlo;
+  cos_hi_lo(th, &x, &xlo);
   ld sh = sinl(0.5L * th), ch = cosl(0.5L * th);
   int64_t l0 = m > 2 ? m : 2;
   for (int64_t l = 0; l < l0 && l <= lmax; ++l) out[l] = 0.0L;
@@ -223,13 +266,31 @@ static void lam_row_spin2(int s, int64_t lmax, int64_t m, ld th, ld* out) {
   ld cur = ldexpl(st.v, (int)(st.e - SCALE_STEP * sc));
   ld prev = 0.0L;
   ld m2 = (ld)m * (ld)m, s2 = 4.0L;
+  if (use_quad(th, lmax)) {
+    q128 qx = cosq((q128)th), qc = cur, qp = 0, qm2 = (q128)m * m, qs2 = 4;
+    for (int64_t l = l0; l <= lmax; ++l) {
+      out[l] = (sc == 0) ? (ld)qc : 0.0L;
+      q128 fl = l, fl1 = l + 1;
+      q128 Cl = (l == l0) ? 0 : sqrtq((fl * fl - qm2) * (fl * fl - qs2) / (fl * fl * (4 * fl * fl - 1)));
+      q128 Cl1 = sqrtq((fl1 * fl1 - qm2) * (fl1 * fl1 - qs2) / (fl1 * fl1 * (4 * fl1 * fl1 - 1)));
+      q128 nx = ((qx + (q128)s * (q128)m / (fl * fl1)) * qc - Cl * qp) / Cl1;
+      qp = qc;
+      qc = nx;
+      if (fabsq(qc) > (q128)BIG && sc < 0) {
+        qc *= (q128)RESCALE_DOWN;
+        qp *= (q128)RESCALE_DOWN;
+        sc += 1;
+      }
+    }
+    return;
+  }
   for (int64_t l = l0; l <= lmax; ++l) {
     out[l] = (sc == 0) ? cur : 0.0L;
     ld fl = (ld)l, fl1 = (ld)(l + 1);
     ld Cl = (l == l0) ? 0.0L
                       : sqrtl((fl * fl - m2) * (fl * fl - s2) / (fl * fl * (4.0L * fl * fl - 1.0L)));
     ld Cl1 = sqrtl((fl1 * fl1 - m2) * (fl1 * fl1 - s2) / (fl1 * fl1 * (4.0L * fl1 * fl1 - 1.0L)));
-    ld nxt = ((x + (ld)s * (ld)m / (fl * fl1)) * cur - Cl * prev) / Cl1;
+    ld nxt = (((x + (ld)s * (ld)m / (fl * fl1)) * cur - Cl * prev) + xlo * cur) / Cl1;
     prev = cur;
     cur = nxt;
     if (fabsl(cur) > BIG && sc < 0) {
@@ -496,8 +557,6 @@ void orc_map2leg(int ncomp, int64_t nm, int64_t nring, const int64_t* nphi, cons
  *   spin 2: P = sum 2a_lm 2Y_lm, M = sum -2a_lm -2Y_lm, 2a=-(E+iB), -2a=-(E-iB),
  *           Q = Re (P+M)/2, U = Re (P-M)/(2i)
  * ---------------------------------------------------------------------------------------- */
-typedef __float128 q128;
-
 static q128 q_fact(int n) {
   q128 r = 1;
   for (int i = 2; i <= n; ++i) r *= i;
@@ -597,3 +656,45 @@ void orc_brute_synth(int spin, int lmax, const double* alm, int64_t npts, const 
 
 /* expose the brute-force harmonic itself for KATs (value at phi=0) */
 double orc_brute_sylm(int s, int l, int m, double theta) { return (double)q_sylm(s, l, m, theta); }
+
+/* ------------------------------------------------------------------------------------------
+ * The same two recurrences in __float128 (113-bit mantissa), for checking the long-double rows above at large l where
+ * no closed form is affordable (tests/test_oracle.py).  Plain quad arithmetic, no extended exponent: returns -1 when
+ * the start value would leave the quad range (large m far from the equator), 0 otherwise.  out as double pairs
+ * (hi, lo) so that the caller gets ~32 digits through a double interface.
+ * ---------------------------------------------------------------------------------------- */
+int orc_lambda_quad(int s, int64_t lmax, int64_t m, double theta, double* out_hi, double* out_lo) {
+  q128 th = theta, x = cosq(th);
+  int64_t l0 = s == 0 ? m : (m > 2 ? m : 2);
+  for (int64_t l = 0; l <= lmax; ++l) out_hi[l] = out_lo[l] = 0.0;
+  if (l0 > lmax) return 0;
+  if (s != 0 && l0 > 800) return -1; /* the factorials of the explicit sum leave the quad range */
+  q128 cur;
+  if (s == 0) {
+    q128 p = (q128)(2 * m + 1) / (4 * M_PIq);
+    for (int64_t k = 1; k <= m; ++k) p *= (q128)(2 * k - 1) / (q128)(2 * k);
+    cur = sqrtq(p) * powq(sinq(th), (q128)m);
+    if (m & 1) cur = -cur;
+  } else {
+    cur = q_sylm(s, (int)l0, (int)m, th); /* explicit Goldberg sum at the first l */
+  }
+  if (!(fabsq(cur) > 0x1p-16000Q)) return cur == 0 && (theta == 0.0) ? 0 : -1;
+  q128 prev = 0, m2 = (q128)m * m, s2 = (q128)s * s;
+  for (int64_t l = l0; l <= lmax; ++l) {
+    out_hi[l] = (double)cur;
+    out_lo[l] = (double)(cur - (q128)out_hi[l]);
+    q128 fl = l, fl1 = l + 1, nxt;
+    if (s == 0) {
+      q128 el = (l == l0) ? 0 : sqrtq((fl * fl - m2) / (4 * fl * fl - 1));
+      q128 el1 = sqrtq((fl1 * fl1 - m2) / (4 * fl1 * fl1 - 1));
+      nxt = (x * cur - el * prev) / el1;
+    } else {
+      q128 Cl = (l == l0) ? 0 : sqrtq((fl * fl - m2) * (fl * fl - s2) / (fl * fl * (4 * fl * fl - 1)));
+      q128 Cl1 = sqrtq((fl1 * fl1 - m2) * (fl1 * fl1 - s2) / (fl1 * fl1 * (4 * fl1 * fl1 - 1)));
+      nxt = ((x + (q128)s * (q128)m / (fl * fl1)) * cur - Cl * prev) / Cl1;
+    }
+    prev = cur;
+    cur = nxt;
+  }
+  return 0;
+}
