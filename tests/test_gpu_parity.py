@@ -458,9 +458,10 @@ def test_large_size_properties(H, O):
         rstart0 = np.concatenate([[0], np.cumsum(nphi)[:-1]]).astype(np.int64)
         ref = O.leg2map(leg, nphi, phi0, rstart0, int(nphi.sum())).astype(np.float64)
         loc = {int(r): (int(s), int(n)) for r, s, n in zip(info["rings"], info["rstart0"], info["nphi"])}
-        # per-ring relative L2 (pixel domain).  The few rings next to the poles carry ~1e-10 local
-        # error in any plain-FP64 recurrence at this lmax (conditioning eps*l/sin(theta))
-        # and hold a vanishing share of the pixels; the rest must sit at the 1e-13 level.
+        # per-ring relative L2 (pixel domain) against the EXACT sum: the oracle does not apply the backend's
+        # m > mlim(theta) ring cut here, so the terms the cut drops (up to ~1e-11 of a ring at lmax 8191, less
+        # here) are part of these numbers and the round-1 bounds are kept.  The class-wise 1e-12 bounds, with
+        # the oracle applying the cut, are asserted in tests/test_gpu_headline.py for this size too.
         per = []
         for r in sel:
             a = list(sel).index(r)
