@@ -7,8 +7,9 @@
 //     csrc/legendre_tables.hpp (X / Y standard forms, DP / DE difference forms), north/south ring
 //     pairing, m > mlim(theta) culling, 2^(800 k) range tracking with a warp-like block of W ring pairs
 //     advancing in lock step;
-//   ring stage (cpu_leg2map / cpu_map2leg): phase shift + alias fold + a plain
-//     mixed-radix / Bluestein complex FFT per ring.
+//   ring stage (cpu_leg2map / cpu_map2leg): phase shift + alias fold + a real FFT per ring through
+//     one half-length complex transform (plain mixed radix, Bluestein for what is left of the length after the
+//     factors 2, 3, 5); plans are built once per length and kept.
 // It is (a) the "port" CPU baseline timed by bench.py and (b) a model of the kernels' arithmetic that
 // can be checked against the long-double oracle without a GPU.  It is NOT ducc: expect ducc's
 // hand-vectorised kernels to be faster.
@@ -18,6 +19,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -28,7 +30,14 @@ using namespace hpsht;
 namespace {
 
 typedef std::complex<double> cd;
-constexpr int W = 16;       // ring pairs advanced together (the "warp")
+#ifndef PORT_NV0
+#define PORT_NV0 4
+#endif
+#ifndef PORT_NV2
+#define PORT_NV2 2
+#endif
+constexpr int NV0 = PORT_NV0;  // SIMD vectors of ring pairs advanced together (the "warp"): spin 0
+constexpr int NV2 = PORT_NV2;  //                                                          spin 2
 constexpr int GROUP = 8;    // steps between range checks
 constexpr int CHUNK = 32;   // table padding (multiple of GROUP)
 constexpr int SC_STEP = 800;
@@ -98,10 +107,22 @@ ClassRanges class_ranges(int spin, const std::vector<Pair>& pairs) {
   return make_class_ranges(spin, (int)pairs.size(), th.data());
 }
 
+// frexp for finite doubles without the library call (zero and subnormals take the library path)
+inline double frexp_fast(double x, int* e) {
+  uint64_t b;
+  std::memcpy(&b, &x, 8);
+  const int ex = (int)((b >> 52) & 0x7ff);
+  if (ex == 0 || ex == 0x7ff) return std::frexp(x, e);
+  *e = ex - 1022;
+  b = (b & ~(0x7ffULL << 52)) | (1022ULL << 52);
+  std::memcpy(&x, &b, 8);
+  return x;
+}
+
 // x^n (n >= 0) as mant * 2^e with mant in [0.5,1) (or 0)
 inline void pow_scaled(double base, int64_t n, double& mant, int64_t& e) {
   int be;
-  double b = std::frexp(base, &be);
+  double b = frexp_fast(base, &be);
   int64_t bexp = be;
   mant = 1.0;
   e = 0;
@@ -110,13 +131,13 @@ inline void pow_scaled(double base, int64_t n, double& mant, int64_t& e) {
       mant *= b;
       e += bexp;
       int t;
-      mant = std::frexp(mant, &t);
+      mant = frexp_fast(mant, &t);
       e += t;
     }
     b *= b;
     bexp *= 2;
     int t;
-    b = std::frexp(b, &t);
+    b = frexp_fast(b, &t);
     bexp += t;
     n >>= 1;
   }
@@ -130,7 +151,7 @@ inline void to_scaled(double v, int64_t e, double& lam, int& sc) {
     return;
   }
   int t;
-  v = std::frexp(v, &t);
+  v = frexp_fast(v, &t);
   e += t;
   if (e >= -400) {
     sc = 0;
@@ -143,33 +164,78 @@ inline void to_scaled(double v, int64_t e, double& lam, int& sc) {
 
 inline double eps_d(int64_t l, int64_t m) { return std::sqrt((double)(l * l - m * m) / (double)(4 * l * l - 1)); }
 
+// ---------------------------------------------------------------------------------------------
+// SIMD plumbing: GCC generic vectors of VL doubles (one AVX-512 register with -march=native; narrower targets get the
+// same code split by the compiler).  The block kernels keep their whole state in NV such vectors held in local
+// variables across the steps of a group -- as arrays on the stack every step paid a store-to-load forward on each
+// accumulator chain (measured: 25 % of the FMA peak before).
+// ---------------------------------------------------------------------------------------------
+constexpr int VL = 8;
+typedef double v8d __attribute__((vector_size(VL * sizeof(double))));
+typedef long long v8i __attribute__((vector_size(VL * sizeof(long long))));
+inline v8d bc(double x) { return v8d{x, x, x, x, x, x, x, x}; }
+inline v8d ld8(const double* p) {
+  v8d r;
+  std::memcpy(&r, p, sizeof r);
+  return r;
+}
+inline void st8(double* p, v8d v) { std::memcpy(p, &v, sizeof v); }
+
+// out[i] = sum of the lanes of in[i], i = 0..7: three shuffle-and-add levels instead of eight horizontal sums
+inline v8d reduce8(const v8d* in) {
+  const v8i a1 = {0, 8, 2, 10, 4, 12, 6, 14}, b1 = {1, 9, 3, 11, 5, 13, 7, 15};
+  const v8i a2 = {0, 1, 8, 9, 4, 5, 12, 13}, b2 = {2, 3, 10, 11, 6, 7, 14, 15};
+  const v8i a3 = {0, 1, 2, 3, 8, 9, 10, 11}, b3 = {4, 5, 6, 7, 12, 13, 14, 15};
+  v8d r[4], q[2];
+  for (int k = 0; k < 4; ++k)
+    r[k] = __builtin_shuffle(in[2 * k], in[2 * k + 1], a1) + __builtin_shuffle(in[2 * k], in[2 * k + 1], b1);
+  for (int k = 0; k < 2; ++k)
+    q[k] = __builtin_shuffle(r[2 * k], r[2 * k + 1], a2) + __builtin_shuffle(r[2 * k], r[2 * k + 1], b2);
+  return __builtin_shuffle(q[0], q[1], a3) + __builtin_shuffle(q[0], q[1], b3);
+}
+// the sums of one group of steps: red[g][t] (t = 0..3) -> acc[4 (n0 + g) + t] += sum of lanes
+inline void flush_group(const v8d* red, double* acc) {
+  static_assert(GROUP == 8, "two steps (x 4 sums) per output vector");
+  for (int q = 0; q < GROUP / 2; ++q) st8(acc + 8 * q, ld8(acc + 8 * q) + reduce8(red + 8 * q));
+}
+
 // one recurrence step: `u` is the value the accumulation uses; DIFF: (u, v) = (value, first difference)
 template <bool DIFF>
-inline void rec_step(double t, double& u, double& v) {
+inline void rec_step(v8d t, v8d& u, v8d& v) {
   if (DIFF) {
-    v = std::fma(t, u, v);
+    v = t * u + v;
     u = u + v;
   } else {
-    const double nx = std::fma(t, u, -v);
+    const v8d nx = t * u - v;
     v = u;
     u = nx;
   }
 }
 
+// does any lane that is still scaled (sc < 0) exceed the rescale threshold?
+template <int WW>
+inline bool needs_rescale(const double* u, const int* sc) {
+  int big = 0;
+#pragma omp simd reduction(| : big)
+  for (int w = 0; w < WW; ++w) big |= (sc[w] < 0) & (std::fabs(u[w]) > SC_BIG);
+  return big != 0;
+}
+
 // ---------------------------------------------------------------------------------------------
-// spin 0, one block of <= W pairs of one class.  ADJ: leg -> acc (4 doubles / step); else stream -> leg.
+// spin 0, one block of <= NV*VL pairs of one class.  ADJ: leg -> acc (4 doubles / step); else stream -> leg.
 // ---------------------------------------------------------------------------------------------
-template <bool ADJ, bool DIFF, bool ALT>
+template <bool ADJ, bool DIFF, bool ALT, int NV>
 void block_s0(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool ysin, int64_t m, int64_t mi, int64_t nm,
               int64_t nring, int64_t npad, const double* cf, double k0, const double* stream, double* acc,
               cd* leg) {
-  double y[W], u[W], v[W], er[W], ei[W], orr[W], oi[W];
-  double ter[W], tei[W], tor[W], toi[W];
-  int sc[W];
-  bool act[W];
+  constexpr int WW = NV * VL;
+  alignas(64) double y[WW], u[WW], v[WW], er[WW], ei[WW], orr[WW], oi[WW];
+  alignas(64) double ter[WW], tei[WW], tor[WW], toi[WW];
+  int sc[WW];
+  bool act[WW];
   bool any_act = false;
   const int nw = (int)(p1 - p0);
-  for (int w = 0; w < W; ++w) {
+  for (int w = 0; w < WW; ++w) {
     const int64_t p = std::min(p0 + w, p1 - 1);
     const Pair& pr = pairs[p];
     act[w] = w < nw && m <= pr.mlim0;
@@ -182,6 +248,7 @@ void block_s0(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool ysin,
     if (!act[w]) u[w] = 0.0, sc[w] = 0;
     v[w] = DIFF ? u[w] : 0.0;
     er[w] = ei[w] = orr[w] = oi[w] = 0.0;
+    ter[w] = tei[w] = tor[w] = toi[w] = 0.0;
     if (ADJ) {
       const cd gN = act[w] ? leg[(0 * nring + pr.irN) * nm + mi] : cd(0, 0);
       const cd gS = (act[w] && pr.irS >= 0) ? leg[(0 * nring + pr.irS) * nm + mi] : cd(0, 0);
@@ -193,55 +260,84 @@ void block_s0(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool ysin,
     }
   }
   if (!any_act) return;
+  v8d Y[NV], U[NV], V[NV], ER[NV], EI[NV], OR[NV], OI[NV];
+  auto load = [&]() {
+    for (int k = 0; k < NV; ++k) {
+      Y[k] = ld8(y + VL * k), U[k] = ld8(u + VL * k), V[k] = ld8(v + VL * k);
+      ER[k] = ld8(er + VL * k), EI[k] = ld8(ei + VL * k), OR[k] = ld8(orr + VL * k), OI[k] = ld8(oi + VL * k);
+    }
+  };
+  auto store = [&]() {
+    for (int k = 0; k < NV; ++k) {
+      st8(u + VL * k, U[k]), st8(v + VL * k, V[k]);
+      st8(er + VL * k, ER[k]), st8(ei + VL * k, EI[k]), st8(orr + VL * k, OR[k]), st8(oi + VL * k, OI[k]);
+    }
+  };
+  auto any_unscaled = [&]() {
+    bool a = false;
+    for (int w = 0; w < WW; ++w) a |= act[w] && (sc[w] == 0);
+    return a;
+  };
+  load();
+  bool any0 = any_unscaled();
+  v8d red[GROUP * 4];
   for (int64_t n0 = 0; n0 < npad; n0 += GROUP) {
-    bool any0 = false;
-    for (int w = 0; w < W; ++w) any0 |= act[w] && (sc[w] == 0);
-    for (int g = 0; g < GROUP; ++g) {
-      const int64_t n = n0 + g;
-      const double a_ = cf[2 * n], b_ = cf[2 * n + 1];
-      const double sg = (ALT && (n & 1)) ? -1.0 : 1.0;
-      if (ADJ) {
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        if (any0) {
-#pragma omp simd reduction(+ : s0, s1, s2, s3)
-          for (int w = 0; w < W; ++w) {
-            const double pv = sg * u[w];
-            s0 += pv * er[w];
-            s1 += pv * ei[w];
-            s2 += pv * orr[w];
-            s3 += pv * oi[w];
+    if (any0) {
+#pragma GCC unroll 8
+      for (int g = 0; g < GROUP; ++g) {
+        const int64_t n = n0 + g;
+        const v8d a_ = bc(cf[2 * n]), b_ = bc(cf[2 * n + 1]);
+        const double sg = (ALT && (n & 1)) ? -1.0 : 1.0;
+        if (ADJ) {
+          v8d s0 = bc(0.0), s1 = s0, s2 = s0, s3 = s0;
+#pragma GCC unroll 4
+          for (int k = 0; k < NV; ++k) {
+            const v8d pv = ALT ? bc(sg) * U[k] : U[k];
+            s0 = pv * ER[k] + s0, s1 = pv * EI[k] + s1, s2 = pv * OR[k] + s2, s3 = pv * OI[k] + s3;
+          }
+          red[4 * g + 0] = s0, red[4 * g + 1] = s1, red[4 * g + 2] = s2, red[4 * g + 3] = s3;
+        } else {
+          const double* s = &stream[4 * n];
+          const v8d s0 = bc(sg * s[0]), s1 = bc(sg * s[1]), s2 = bc(sg * s[2]), s3 = bc(sg * s[3]);
+#pragma GCC unroll 4
+          for (int k = 0; k < NV; ++k) {
+            ER[k] = U[k] * s0 + ER[k], EI[k] = U[k] * s1 + EI[k];
+            OR[k] = U[k] * s2 + OR[k], OI[k] = U[k] * s3 + OI[k];
           }
         }
-        for (int w = 0; w < W; ++w) rec_step<DIFF>(std::fma(a_, y[w], b_), u[w], v[w]);
-        double* d = &acc[4 * n];
-        d[0] += s0, d[1] += s1, d[2] += s2, d[3] += s3;
-      } else {
-        const double* s = &stream[4 * n];
-        for (int w = 0; w < W; ++w) {
-          if (any0) {
-            const double pv = sg * u[w];
-            er[w] = std::fma(pv, s[0], er[w]);
-            ei[w] = std::fma(pv, s[1], ei[w]);
-            orr[w] = std::fma(pv, s[2], orr[w]);
-            oi[w] = std::fma(pv, s[3], oi[w]);
-          }
-          rec_step<DIFF>(std::fma(a_, y[w], b_), u[w], v[w]);
-        }
+#pragma GCC unroll 4
+        for (int k = 0; k < NV; ++k) rec_step<DIFF>(a_ * Y[k] + b_, U[k], V[k]);
+      }
+      if (ADJ) flush_group(red, acc + 4 * n0);
+    } else {
+#pragma GCC unroll 8
+      for (int g = 0; g < GROUP; ++g) {
+        const int64_t n = n0 + g;
+        const v8d a_ = bc(cf[2 * n]), b_ = bc(cf[2 * n + 1]);
+#pragma GCC unroll 4
+        for (int k = 0; k < NV; ++k) rec_step<DIFF>(a_ * Y[k] + b_, U[k], V[k]);
       }
     }
-    for (int w = 0; w < W; ++w) {
-      if (sc[w] < 0 && std::fabs(u[w]) > SC_BIG) {
-        u[w] *= SC_DOWN;
-        v[w] *= SC_DOWN;
-        sc[w] += 1;
-        if (ADJ) {
-          if (sc[w] == 0) er[w] = ter[w], ei[w] = tei[w], orr[w] = tor[w], oi[w] = toi[w];
-        } else {
-          er[w] = ei[w] = orr[w] = oi[w] = 0.0;  // drop what was accumulated while scaled
+    for (int k = 0; k < NV; ++k) st8(u + VL * k, U[k]);
+    if (needs_rescale<WW>(u, sc)) {
+      store();
+      for (int w = 0; w < WW; ++w) {
+        if (sc[w] < 0 && std::fabs(u[w]) > SC_BIG) {
+          u[w] *= SC_DOWN;
+          v[w] *= SC_DOWN;
+          sc[w] += 1;
+          if (ADJ) {
+            if (sc[w] == 0) er[w] = ter[w], ei[w] = tei[w], orr[w] = tor[w], oi[w] = toi[w];
+          } else {
+            er[w] = ei[w] = orr[w] = oi[w] = 0.0;  // drop what was accumulated while scaled
+          }
         }
       }
+      load();
+      any0 = any_unscaled();
     }
   }
+  store();
   if (!ADJ)
     for (int w = 0; w < nw; ++w) {
       const Pair& pr = pairs[p0 + w];
@@ -253,18 +349,20 @@ void block_s0(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool ysin,
 }
 
 // ---------------------------------------------------------------------------------------------
-// spin 2, one block of <= W pairs of one class
+// spin 2, one block of <= NV*VL pairs of one class
 // ---------------------------------------------------------------------------------------------
-template <bool ADJ, bool DIFF>
+template <bool ADJ, bool DIFF, int NV>
 void block_s2(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool yform, int64_t m, int64_t mi, int64_t nm,
               int64_t nring, int64_t npad, const double* ca, const double* cf, double kp, double km,
               const double* stream, double* acc, cd* leg) {
-  double y[W], up[W], vp[W], um[W], vm[W];
-  cd PpN[W], PmN[W], PpS[W], PmS[W];              // synthesis accumulators
-  cd twpN[W], twmN[W], twpS[W], twmS[W];          // adjoint: true inputs
-  cd wpN[W], wmN[W], wpS[W], wmS[W];              // adjoint: masked by the scale state of the lam they multiply
-  int scp[W], scm[W];
-  bool act[W];
+  constexpr int WW = NV * VL;
+  alignas(64) double y[WW], up[WW], vp[WW], um[WW], vm[WW];
+  // synthesis: the four complex accumulators P+N, P-N, P+S, P-S; adjoint: the four complex inputs w+N, w-N, w+S,
+  // w-S masked by the scale state of the lambda they multiply.  Slot order: 0 +N, 1 -N, 2 +S, 3 -S (re, im apart).
+  alignas(64) double zr[4][WW], zi[4][WW];
+  alignas(64) double tr[4][WW], ti[4][WW];   // adjoint: the true inputs
+  int scp[WW], scm[WW];
+  bool act[WW];
   bool any_act = false;
   const int nw = (int)(p1 - p0);
   const int64_t pw = m >= 2 ? m - 2 : 2 - m;
@@ -272,7 +370,7 @@ void block_s2(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool yform
   const int64_t l0 = m > 2 ? m : 2;
   const bool odd0 = ((l0 + m) & 1) != 0;  // parity of (l+m) at the first step
   const cd I(0, 1);
-  for (int w = 0; w < W; ++w) {
+  for (int w = 0; w < WW; ++w) {
     const int64_t p = std::min(p0 + w, p1 - 1);
     const Pair& pr = pairs[p];
     act[w] = w < nw && m <= pr.mlim2;
@@ -291,92 +389,115 @@ void block_s2(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool yform
     if (!act[w]) up[w] = um[w] = 0.0, scp[w] = scm[w] = 0;
     vp[w] = DIFF ? up[w] : 0.0;
     vm[w] = DIFF ? um[w] : 0.0;
-    PpN[w] = PmN[w] = PpS[w] = PmS[w] = 0;
+    for (int t = 0; t < 4; ++t) zr[t][w] = zi[t][w] = tr[t][w] = ti[t][w] = 0.0;
     if (ADJ) {
       const cd qN = act[w] ? leg[(0 * nring + pr.irN) * nm + mi] : cd(0, 0);
       const cd uN = act[w] ? leg[(1 * nring + pr.irN) * nm + mi] : cd(0, 0);
       const cd qS = (act[w] && pr.irS >= 0) ? leg[(0 * nring + pr.irS) * nm + mi] : cd(0, 0);
       const cd uS = (act[w] && pr.irS >= 0) ? leg[(1 * nring + pr.irS) * nm + mi] : cd(0, 0);
-      twpN[w] = qN + I * uN;
-      twmN[w] = qN - I * uN;
-      twpS[w] = qS + I * uS;
-      twmS[w] = qS - I * uS;
+      const cd tw[4] = {qN + I * uN, qN - I * uN, qS + I * uS, qS - I * uS};
+      for (int t = 0; t < 4; ++t) tr[t][w] = tw[t].real(), ti[t][w] = tw[t].imag();
       // G+ += lam+ w+N + sgn lam- w+S ; G- += lam- w-N + sgn lam+ w-S
-      wpN[w] = scp[w] == 0 ? twpN[w] : cd(0, 0);
-      wmS[w] = scp[w] == 0 ? twmS[w] : cd(0, 0);
-      wmN[w] = scm[w] == 0 ? twmN[w] : cd(0, 0);
-      wpS[w] = scm[w] == 0 ? twpS[w] : cd(0, 0);
+      if (scp[w] == 0) zr[0][w] = tr[0][w], zi[0][w] = ti[0][w], zr[3][w] = tr[3][w], zi[3][w] = ti[3][w];
+      if (scm[w] == 0) zr[1][w] = tr[1][w], zi[1][w] = ti[1][w], zr[2][w] = tr[2][w], zi[2][w] = ti[2][w];
     }
   }
   if (!any_act) return;
+  v8d Y[NV], UP[NV], VP[NV], UM[NV], VM[NV], ZR[4][NV], ZI[4][NV];
+  auto load = [&]() {
+    for (int k = 0; k < NV; ++k) {
+      Y[k] = ld8(y + VL * k);
+      UP[k] = ld8(up + VL * k), VP[k] = ld8(vp + VL * k), UM[k] = ld8(um + VL * k), VM[k] = ld8(vm + VL * k);
+      for (int t = 0; t < 4; ++t) ZR[t][k] = ld8(zr[t] + VL * k), ZI[t][k] = ld8(zi[t] + VL * k);
+    }
+  };
+  auto store = [&]() {
+    for (int k = 0; k < NV; ++k) {
+      st8(up + VL * k, UP[k]), st8(vp + VL * k, VP[k]), st8(um + VL * k, UM[k]), st8(vm + VL * k, VM[k]);
+      for (int t = 0; t < 4; ++t) st8(zr[t] + VL * k, ZR[t][k]), st8(zi[t] + VL * k, ZI[t][k]);
+    }
+  };
+  auto any_unscaled = [&]() {
+    bool a = false;
+    for (int w = 0; w < WW; ++w) a |= act[w] && ((scp[w] == 0) | (scm[w] == 0));
+    return a;
+  };
+  load();
+  bool any0 = any_unscaled();
+  v8d red[GROUP * 4];
   for (int64_t n0 = 0; n0 < npad; n0 += GROUP) {
-    bool any0 = false;
-    for (int w = 0; w < W; ++w) any0 |= act[w] && ((scp[w] == 0) | (scm[w] == 0));
+#pragma GCC unroll 8
     for (int g = 0; g < GROUP; ++g) {
       const int64_t j = n0 + g;
-      const double a_ = ca[j], cp = cf[2 * j], cm = cf[2 * j + 1];
+      const v8d a_ = bc(ca[j]), cp = bc(cf[2 * j]), cm = bc(cf[2 * j + 1]);
       const double sgn = (odd0 ^ ((j & 1) != 0)) ? -1.0 : 1.0;
-      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-      const double* s = ADJ ? nullptr : &stream[4 * j];
-      if (ADJ && any0) {
-        const double* ap = reinterpret_cast<const double*>(wpN);   // (re, im) pairs
-        const double* bp = reinterpret_cast<const double*>(wpS);
-        const double* cp2 = reinterpret_cast<const double*>(wmN);
-        const double* dp = reinterpret_cast<const double*>(wmS);
-#pragma omp simd reduction(+ : s0, s1, s2, s3)
-        for (int w = 0; w < W; ++w) {
-          const double sm_ = sgn * um[w], sp_ = sgn * up[w];
-          s0 += up[w] * ap[2 * w] + sm_ * bp[2 * w];
-          s1 += up[w] * ap[2 * w + 1] + sm_ * bp[2 * w + 1];
-          s2 += um[w] * cp2[2 * w] + sp_ * dp[2 * w];
-          s3 += um[w] * cp2[2 * w + 1] + sp_ * dp[2 * w + 1];
-        }
-      }
-      for (int w = 0; w < W; ++w) {
-        if (any0) {
-          if (ADJ) {
-          } else {
-            PpN[w] = cd(std::fma(up[w], s[0], PpN[w].real()), std::fma(up[w], s[1], PpN[w].imag()));
-            PmN[w] = cd(std::fma(um[w], s[2], PmN[w].real()), std::fma(um[w], s[3], PmN[w].imag()));
-            PpS[w] = cd(std::fma(sgn * um[w], s[0], PpS[w].real()), std::fma(sgn * um[w], s[1], PpS[w].imag()));
-            PmS[w] = cd(std::fma(sgn * up[w], s[2], PmS[w].real()), std::fma(sgn * up[w], s[3], PmS[w].imag()));
+      if (any0) {
+        if (ADJ) {
+          v8d s0 = bc(0.0), s1 = s0, s2 = s0, s3 = s0;
+          const v8d sg = bc(sgn);
+#pragma GCC unroll 4
+          for (int k = 0; k < NV; ++k) {
+            const v8d sm_ = sg * UM[k], sp_ = sg * UP[k];
+            s0 = UP[k] * ZR[0][k] + (sm_ * ZR[2][k] + s0);
+            s1 = UP[k] * ZI[0][k] + (sm_ * ZI[2][k] + s1);
+            s2 = UM[k] * ZR[1][k] + (sp_ * ZR[3][k] + s2);
+            s3 = UM[k] * ZI[1][k] + (sp_ * ZI[3][k] + s3);
+          }
+          red[4 * g + 0] = s0, red[4 * g + 1] = s1, red[4 * g + 2] = s2, red[4 * g + 3] = s3;
+        } else {
+          const double* s = &stream[4 * j];
+          const v8d s0 = bc(s[0]), s1 = bc(s[1]), s2 = bc(s[2]), s3 = bc(s[3]);
+          const v8d t0 = bc(sgn * s[0]), t1 = bc(sgn * s[1]), t2 = bc(sgn * s[2]), t3 = bc(sgn * s[3]);
+#pragma GCC unroll 4
+          for (int k = 0; k < NV; ++k) {
+            ZR[0][k] = UP[k] * s0 + ZR[0][k], ZI[0][k] = UP[k] * s1 + ZI[0][k];   // P+N
+            ZR[1][k] = UM[k] * s2 + ZR[1][k], ZI[1][k] = UM[k] * s3 + ZI[1][k];   // P-N
+            ZR[2][k] = UM[k] * t0 + ZR[2][k], ZI[2][k] = UM[k] * t1 + ZI[2][k];   // P+S
+            ZR[3][k] = UP[k] * t2 + ZR[3][k], ZI[3][k] = UP[k] * t3 + ZI[3][k];   // P-S
           }
         }
-        rec_step<DIFF>(std::fma(a_, y[w], cp), up[w], vp[w]);
-        rec_step<DIFF>(std::fma(a_, y[w], cm), um[w], vm[w]);
       }
-      if (ADJ) {
-        double* d = &acc[4 * j];
-        d[0] += s0, d[1] += s1, d[2] += s2, d[3] += s3;
+#pragma GCC unroll 4
+      for (int k = 0; k < NV; ++k) {
+        rec_step<DIFF>(a_ * Y[k] + cp, UP[k], VP[k]);
+        rec_step<DIFF>(a_ * Y[k] + cm, UM[k], VM[k]);
       }
     }
-    for (int w = 0; w < W; ++w) {
-      if (scp[w] < 0 && std::fabs(up[w]) > SC_BIG) {
-        up[w] *= SC_DOWN;
-        vp[w] *= SC_DOWN;
-        scp[w] += 1;
-        if (ADJ) {
-          if (scp[w] == 0) wpN[w] = twpN[w], wmS[w] = twmS[w];
-        } else {
-          PpN[w] = PmS[w] = 0;
+    if (ADJ && any0) flush_group(red, acc + 4 * n0);
+    for (int k = 0; k < NV; ++k) st8(up + VL * k, UP[k]), st8(um + VL * k, UM[k]);
+    if (needs_rescale<WW>(up, scp) || needs_rescale<WW>(um, scm)) {
+      store();
+      for (int w = 0; w < WW; ++w) {
+        if (scp[w] < 0 && std::fabs(up[w]) > SC_BIG) {
+          up[w] *= SC_DOWN;
+          vp[w] *= SC_DOWN;
+          scp[w] += 1;
+          if (ADJ) {
+            if (scp[w] == 0) zr[0][w] = tr[0][w], zi[0][w] = ti[0][w], zr[3][w] = tr[3][w], zi[3][w] = ti[3][w];
+          } else {
+            zr[0][w] = zi[0][w] = zr[3][w] = zi[3][w] = 0.0;
+          }
+        }
+        if (scm[w] < 0 && std::fabs(um[w]) > SC_BIG) {
+          um[w] *= SC_DOWN;
+          vm[w] *= SC_DOWN;
+          scm[w] += 1;
+          if (ADJ) {
+            if (scm[w] == 0) zr[1][w] = tr[1][w], zi[1][w] = ti[1][w], zr[2][w] = tr[2][w], zi[2][w] = ti[2][w];
+          } else {
+            zr[1][w] = zi[1][w] = zr[2][w] = zi[2][w] = 0.0;
+          }
         }
       }
-      if (scm[w] < 0 && std::fabs(um[w]) > SC_BIG) {
-        um[w] *= SC_DOWN;
-        vm[w] *= SC_DOWN;
-        scm[w] += 1;
-        if (ADJ) {
-          if (scm[w] == 0) wmN[w] = twmN[w], wpS[w] = twpS[w];
-        } else {
-          PmN[w] = PpS[w] = 0;
-        }
-      }
+      load();
+      any0 = any_unscaled();
     }
   }
+  store();
   if (!ADJ)
     for (int w = 0; w < nw; ++w) {
       const Pair& pr = pairs[p0 + w];
-      cd a = PpN[w], b = PmN[w], c = PpS[w], d = PmS[w];
+      cd a(zr[0][w], zi[0][w]), b(zr[1][w], zi[1][w]), c(zr[2][w], zi[2][w]), d(zr[3][w], zi[3][w]);
       if (!act[w] || scp[w] < 0) a = 0, d = 0;
       if (!act[w] || scm[w] < 0) b = 0, c = 0;
       const cd mi_(0, -1);
@@ -389,36 +510,38 @@ void block_s2(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool yform
     }
 }
 
-// all classes of one m
+// all classes of one m.  T holds the tables of this m alone (built by the calling thread); mi is the column of
+// the leg array.
 template <bool ADJ>
 void run_m(int spin, const LegendreTables& T, const std::vector<Pair>& pairs, const ClassRanges& cr, int64_t mi,
            int64_t nm, int64_t nring, const double* stream, double* acc, cd* leg) {
-  const int64_t m = T.mval[(size_t)mi];
+  const int64_t m = T.mval[0];
   for (int c = 0; c < LC_COUNT; ++c) {
     if (spin != 0 && c == LC_DE) continue;
     const bool yside = (c == LC_Y || c == LC_DP);
+    const int W = (spin == 0 ? NV0 : NV2) * VL;
     for (int64_t p0 = cr.lo(c); p0 < cr.hi(c); p0 += W) {
       const int64_t p1 = std::min<int64_t>(p0 + W, cr.hi(c));
       if (spin == 0) {
-        const int64_t npad = round_up(T.nstep0[(size_t)mi], CHUNK);
-        const double* cf = &T.coef0[c][(size_t)T.coff0[c][(size_t)mi] * 2];
-        const double k0 = T.k0[(size_t)mi];
+        const int64_t npad = round_up(T.nstep0[0], CHUNK);
+        const double* cf = &T.coef0[c][(size_t)T.coff0[c][0] * 2];
+        const double k0 = T.k0[0];
         if (c == LC_DE)
-          block_s0<ADJ, true, true>(pairs, p0, p1, false, m, mi, nm, nring, npad, cf, k0, stream, acc, leg);
+          block_s0<ADJ, true, true, NV0>(pairs, p0, p1, false, m, mi, nm, nring, npad, cf, k0, stream, acc, leg);
         else if (c == LC_DP)
-          block_s0<ADJ, true, false>(pairs, p0, p1, true, m, mi, nm, nring, npad, cf, k0, stream, acc, leg);
+          block_s0<ADJ, true, false, NV0>(pairs, p0, p1, true, m, mi, nm, nring, npad, cf, k0, stream, acc, leg);
         else
-          block_s0<ADJ, false, false>(pairs, p0, p1, yside, m, mi, nm, nring, npad, cf, k0, stream, acc, leg);
+          block_s0<ADJ, false, false, NV0>(pairs, p0, p1, yside, m, mi, nm, nring, npad, cf, k0, stream, acc, leg);
       } else {
-        const int64_t npad = round_up(T.nstep2[(size_t)mi], CHUNK);
-        const double* ca = &T.coefa2[(size_t)T.off2[(size_t)mi]];
-        const double* cf = &T.coef2[c][(size_t)T.coff2[c][(size_t)mi] * 2];
+        const int64_t npad = round_up(T.nstep2[0], CHUNK);
+        const double* ca = &T.coefa2[(size_t)T.off2[0]];
+        const double* cf = &T.coef2[c][(size_t)T.coff2[c][0] * 2];
         if (c == LC_DP)
-          block_s2<ADJ, true>(pairs, p0, p1, true, m, mi, nm, nring, npad, ca, cf, T.kp2[(size_t)mi], T.km2[(size_t)mi],
-                              stream, acc, leg);
+          block_s2<ADJ, true, NV2>(pairs, p0, p1, true, m, mi, nm, nring, npad, ca, cf, T.kp2[0], T.km2[0], stream,
+                                   acc, leg);
         else
-          block_s2<ADJ, false>(pairs, p0, p1, yside, m, mi, nm, nring, npad, ca, cf, T.kp2[(size_t)mi],
-                               T.km2[(size_t)mi], stream, acc, leg);
+          block_s2<ADJ, false, NV2>(pairs, p0, p1, yside, m, mi, nm, nring, npad, ca, cf, T.kp2[0], T.km2[0],
+                                    stream, acc, leg);
       }
     }
   }
@@ -435,8 +558,7 @@ struct FftPlan {
   int64_t leaf = 0;           // n with the factors 2, 3, 5 removed, when that has a prime factor > 64 (else 0)
   int64_t M = 0;              // Bluestein length for the leaf (power of two >= 2 leaf - 1)
   std::vector<cd> chirp, chirpF;
-  FftPlan* sub = nullptr;     // plan of length M
-  ~FftPlan() { delete sub; }
+  const FftPlan* sub = nullptr;  // plan of length M (owned by the plan store, shared by every leaf of that M)
 };
 void fft_rec(const FftPlan& P, const cd* in, int64_t istride, cd* out, int64_t n, int64_t wstride, std::vector<cd>& work);
 // leaf DFT by Bluestein: out[k] = sum_j in[j istride] exp(-2 pi i jk / L)
@@ -503,12 +625,9 @@ void fft_rec(const FftPlan& P, const cd* in, int64_t istride, cd* out, int64_t n
     }
   }
 }
-FftPlan* make_plan(int64_t n) {
-  FftPlan* P = new FftPlan();
-  P->n = n;
-  const long double tp = 2.0L * LT_PI / (long double)n;
-  P->w.resize((size_t)n);
-  for (int64_t k = 0; k < n; ++k) P->w[(size_t)k] = cd((double)cosl(tp * k), (double)-sinl(tp * k));
+// exp(-2 pi i k / n), k = 0 .. count-1
+void fill_twiddles(int64_t n, int64_t count, std::vector<cd>& w);
+int64_t bluestein_leaf_of(int64_t n) {  // n with 2, 3, 5 removed when that keeps a prime factor > 64, else 0
   int64_t L = n;
   for (int64_t p : {2, 3, 5})
     while (L % p == 0) L /= p;
@@ -516,17 +635,26 @@ FftPlan* make_plan(int64_t n) {
   for (int64_t p = 7; p * p <= t; p += 2)
     while (t % p == 0) big = std::max(big, p), t /= p;
   big = std::max(big, t);
-  if (L > 1 && big > 64) {
+  return (L > 1 && big > 64) ? L : 0;
+}
+int64_t bluestein_len(int64_t L) {
+  int64_t M = 1;
+  while (M < 2 * L - 1) M *= 2;
+  return M;
+}
+FftPlan* make_plan(int64_t n, const FftPlan* sub) {
+  FftPlan* P = new FftPlan();
+  P->n = n;
+  fill_twiddles(n, n, P->w);
+  const int64_t L = bluestein_leaf_of(n);
+  if (L) {
     P->leaf = L;
-    P->M = 1;
-    while (P->M < 2 * L - 1) P->M *= 2;
-    P->sub = make_plan(P->M);
+    P->M = bluestein_len(L);
+    P->sub = sub;
+    std::vector<cd> w2;
+    fill_twiddles(2 * L, 2 * L, w2);   // exp(-i pi q / L)
     P->chirp.resize((size_t)L);
-    for (int64_t k = 0; k < L; ++k) {
-      const int64_t kk = (k * k) % (2 * L);
-      const long double a = LT_PI * (long double)kk / (long double)L;
-      P->chirp[(size_t)k] = cd((double)cosl(a), (double)-sinl(a));
-    }
+    for (int64_t k = 0; k < L; ++k) P->chirp[(size_t)k] = w2[(size_t)((k * k) % (2 * L))];
     std::vector<cd> b((size_t)P->M, cd(0, 0)), wk;
     for (int64_t k = 0; k < L; ++k) {
       b[(size_t)k] = std::conj(P->chirp[(size_t)k]);
@@ -537,30 +665,132 @@ FftPlan* make_plan(int64_t n) {
   }
   return P;
 }
+// exp(-2 pi i k / n) = A[k / S] * B[k % S]: 2 sqrt(n) long-double evaluations and `count` long-double products, each
+// entry still within an ulp (the product is formed in 64-bit mantissas before rounding)
+void fill_twiddles(int64_t n, int64_t count, std::vector<cd>& w) {
+  const long double tp = 2.0L * LT_PI / (long double)n;
+  w.resize((size_t)count);
+  int64_t S = 1;
+  while (S * S < count) S *= 2;
+  std::vector<long double> ac((size_t)((count + S - 1) / S)), as(ac.size()), bcs((size_t)S), bsn((size_t)S);
+  for (size_t i = 0; i < ac.size(); ++i) ac[i] = cosl(tp * (long double)(i * S)), as[i] = sinl(tp * (long double)(i * S));
+  for (int64_t j = 0; j < S; ++j) bcs[(size_t)j] = cosl(tp * (long double)j), bsn[(size_t)j] = sinl(tp * (long double)j);
+  for (int64_t k = 0; k < count; ++k) {
+    const size_t i = (size_t)(k / S), j = (size_t)(k % S);
+    w[(size_t)k] = cd((double)(ac[i] * bcs[j] - as[i] * bsn[j]), (double)-(as[i] * bcs[j] + ac[i] * bsn[j]));
+  }
+}
 // forward DFT (e^{-i}); inverse via conjugation by the caller
 void fft_fwd(const FftPlan& P, const cd* in, cd* out, std::vector<cd>& work) {
   work.clear();
   fft_rec(P, in, 1, out, P.n, 1, work);
 }
 
-struct PlanCache {
-  std::vector<int64_t> lens;
-  std::vector<FftPlan*> plans;
-  const FftPlan& get(int64_t n) const {
-    const size_t i = (size_t)(std::lower_bound(lens.begin(), lens.end(), n) - lens.begin());
-    return *plans[i];
+// A ring of n = 2h real points is transformed through ONE complex FFT of length h (even / odd samples packed as
+// real / imaginary part) plus a split pass.
+struct RingPlan {
+  int64_t n = 0;
+  const FftPlan* half = nullptr;   // length n / 2
+  std::vector<cd> wn;              // exp(-2 pi i k / n), k = 0 .. n/2
+};
+// Plans live for the life of the process (a production library keeps its plans between calls too); lookups after
+// prepare() are read-only.
+struct PlanStore {
+  std::vector<int64_t> flen, rlen;   // sorted keys
+  std::vector<FftPlan*> fplan;
+  std::vector<RingPlan*> rplan;
+  const FftPlan* fft(int64_t n) const {
+    const size_t i = (size_t)(std::lower_bound(flen.begin(), flen.end(), n) - flen.begin());
+    return (i < flen.size() && flen[i] == n) ? fplan[i] : nullptr;
   }
-  ~PlanCache() {
-    for (auto* p : plans) delete p;
+  const RingPlan* ring(int64_t n) const {
+    const size_t i = (size_t)(std::lower_bound(rlen.begin(), rlen.end(), n) - rlen.begin());
+    return (i < rlen.size() && rlen[i] == n) ? rplan[i] : nullptr;
+  }
+  template <class T>
+  static void merge(std::vector<int64_t>& keys, std::vector<T*>& vals, const std::vector<int64_t>& nk,
+                    const std::vector<T*>& nv) {
+    std::vector<std::pair<int64_t, T*>> all;
+    for (size_t i = 0; i < keys.size(); ++i) all.emplace_back(keys[i], vals[i]);
+    for (size_t i = 0; i < nk.size(); ++i) all.emplace_back(nk[i], nv[i]);
+    std::sort(all.begin(), all.end());
+    keys.clear(), vals.clear();
+    for (auto& kv : all) keys.push_back(kv.first), vals.push_back(kv.second);
+  }
+  // make sure a ring plan exists for every length in nphi (all even)
+  void prepare(int64_t nring, const int64_t* nphi) {
+    std::vector<int64_t> want(nphi, nphi + nring);
+    std::sort(want.begin(), want.end());
+    want.erase(std::unique(want.begin(), want.end()), want.end());
+    std::vector<int64_t> miss;
+    for (int64_t n : want)
+      if (!ring(n)) miss.push_back(n);
+    if (miss.empty()) return;
+    // the power-of-two transforms behind the Bluestein leaves first (a handful), then the half-length plans
+    std::vector<int64_t> subs;
+    for (int64_t n : miss) {
+      const int64_t L = bluestein_leaf_of(n / 2);
+      if (L && !fft(bluestein_len(L))) subs.push_back(bluestein_len(L));
+    }
+    std::sort(subs.begin(), subs.end());
+    subs.erase(std::unique(subs.begin(), subs.end()), subs.end());
+    std::vector<FftPlan*> sp(subs.size());
+    for (size_t i = 0; i < subs.size(); ++i) sp[i] = make_plan(subs[i], nullptr);
+    merge(flen, fplan, subs, sp);
+    std::vector<int64_t> halves;
+    for (int64_t n : miss)
+      if (!fft(n / 2)) halves.push_back(n / 2);
+    std::vector<FftPlan*> hp(halves.size());
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < (int64_t)halves.size(); ++i) {
+      const int64_t L = bluestein_leaf_of(halves[(size_t)i]);
+      hp[(size_t)i] = make_plan(halves[(size_t)i], L ? fft(bluestein_len(L)) : nullptr);
+    }
+    merge(flen, fplan, halves, hp);
+    std::vector<RingPlan*> rp(miss.size());
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < (int64_t)miss.size(); ++i) {
+      RingPlan* R = new RingPlan();
+      R->n = miss[(size_t)i];
+      R->half = fft(R->n / 2);
+      fill_twiddles(R->n, R->n / 2 + 1, R->wn);
+      rp[(size_t)i] = R;
+    }
+    merge(rlen, rplan, miss, rp);
   }
 };
-void build_cache(PlanCache& pc, int64_t nring, const int64_t* nphi) {
-  pc.lens.assign(nphi, nphi + nring);
-  std::sort(pc.lens.begin(), pc.lens.end());
-  pc.lens.erase(std::unique(pc.lens.begin(), pc.lens.end()), pc.lens.end());
-  pc.plans.resize(pc.lens.size());
-#pragma omp parallel for schedule(dynamic, 1)
-  for (int64_t i = 0; i < (int64_t)pc.lens.size(); ++i) pc.plans[(size_t)i] = make_plan(pc.lens[(size_t)i]);
+PlanStore g_plans;
+
+// x[0..n) real from the half-complex spectrum hc[0..n/2] (Im hc[0], Im hc[n/2] ignored):
+//   x[j] = sum_{k=0}^{n-1} F[k] e^{+2 pi i jk/n},  F[k] = hc[k] (k <= n/2), F[n-k] = conj(hc[k])
+// Z[k] = (F[k] + conj(F[h-k])) + i e^{+2 pi i k/n} (F[k] - conj(F[h-k])),  z = IDFT_h(Z),  x[2j] + i x[2j+1] = z[j]
+void ring_c2r(const RingPlan& R, const cd* hc, double* x, std::vector<cd>& a, std::vector<cd>& b, std::vector<cd>& work) {
+  const int64_t h = R.n / 2;
+  a.resize((size_t)h);
+  b.resize((size_t)h);
+  for (int64_t k = 0; k < h; ++k) {
+    const cd Fk = k == 0 ? cd(hc[0].real(), 0) : hc[k];
+    const cd Fq = std::conj(k == 0 ? cd(hc[h].real(), 0) : hc[h - k]);
+    const cd s = Fk + Fq, d = (Fk - Fq) * std::conj(R.wn[(size_t)k]);   // conj(wn) = e^{+2 pi i k/n}
+    const cd Z = s + cd(-d.imag(), d.real());
+    a[(size_t)k] = std::conj(Z);   // inverse transform through the forward one
+  }
+  fft_fwd(*R.half, a.data(), b.data(), work);
+  for (int64_t j = 0; j < h; ++j) x[2 * j] = b[(size_t)j].real(), x[2 * j + 1] = -b[(size_t)j].imag();
+}
+// X[k] = sum_j x[j] e^{-2 pi i jk/n} for k = 0 .. n/2 from the real x[0..n)
+void ring_r2c(const RingPlan& R, const double* x, cd* X, std::vector<cd>& a, std::vector<cd>& b, std::vector<cd>& work) {
+  const int64_t h = R.n / 2;
+  a.resize((size_t)h);
+  b.resize((size_t)h);
+  for (int64_t j = 0; j < h; ++j) a[(size_t)j] = cd(x[2 * j], x[2 * j + 1]);
+  fft_fwd(*R.half, a.data(), b.data(), work);
+  for (int64_t k = 0; k <= h; ++k) {
+    const cd Zk = b[(size_t)(k == h ? 0 : k)], Zq = std::conj(b[(size_t)(k == 0 ? 0 : h - k)]);
+    const cd E = 0.5 * (Zk + Zq), D = Zk - Zq;          // O = D / (2i)
+    const cd O(0.5 * D.imag(), -0.5 * D.real());
+    X[k] = E + R.wn[(size_t)k] * O;
+  }
 }
 
 }  // namespace
@@ -597,19 +827,19 @@ void cpu_alm2leg(int spin, int64_t lmax, int64_t nm, const int64_t* mval, const 
   const int ncomp = spin ? 2 : 1;
   std::vector<Pair> pairs = make_pairs(lmax, nring, theta);
   const ClassRanges cr = class_ranges(spin, pairs);
-  LegendreTables T;
-  build_legendre_tables(lmax, mval, nm, CHUNK, spin == 0, spin != 0, T);
   std::memset(leg_, 0, sizeof(double) * 2 * (size_t)ncomp * nring * nm);
 #pragma omp parallel
   {
     std::vector<double> stream;  // per-m prepared alm stream
+    LegendreTables T;            // per-m coefficient tables, built by the thread that uses them
 #pragma omp for schedule(dynamic, 1)
     for (int64_t mi = 0; mi < nm; ++mi) {
       const int64_t m = mval[mi];
+      build_legendre_tables(lmax, &m, 1, CHUNK, spin == 0, spin != 0, T);
       if (spin == 0) {
-        const int64_t nn = T.nstep0[mi];
+        const int64_t nn = T.nstep0[0];
         if (nn == 0) continue;
-        const double* is = &T.invs0[(size_t)T.off0[mi]];
+        const double* is = &T.invs0[0];
         stream.assign((size_t)round_up(nn, CHUNK) * 4, 0.0);
         const cd* a = alm + mstart[mi];
         for (int64_t n = 0; n < nn; ++n) {  // Ae_n, Ao_n
@@ -625,10 +855,10 @@ void cpu_alm2leg(int spin, int64_t lmax, int64_t nm, const int64_t* mval, const 
           stream[4 * n + 3] = B.imag();
         }
       } else {
-        const int64_t nl = T.nstep2[mi];
+        const int64_t nl = T.nstep2[0];
         if (nl == 0) continue;
         const int64_t l0 = m > 2 ? m : 2;
-        const double* sg = &T.sig2[(size_t)T.off2[mi]];
+        const double* sg = &T.sig2[0];
         stream.assign((size_t)round_up(nl, CHUNK) * 4, 0.0);
         const cd* ea = alm + mstart[mi];
         const cd* ba = alm + alm_cstride + mstart[mi];
@@ -657,18 +887,18 @@ void cpu_leg2alm(int spin, int64_t lmax, int64_t nm, const int64_t* mval, const 
   cd* alm = reinterpret_cast<cd*>(alm_);
   std::vector<Pair> pairs = make_pairs(lmax, nring, theta);
   const ClassRanges cr = class_ranges(spin, pairs);
-  LegendreTables T;
-  build_legendre_tables(lmax, mval, nm, CHUNK, spin == 0, spin != 0, T);
 #pragma omp parallel
   {
     std::vector<double> acc;
+    LegendreTables T;
 #pragma omp for schedule(dynamic, 1)
     for (int64_t mi = 0; mi < nm; ++mi) {
       const int64_t m = mval[mi];
+      build_legendre_tables(lmax, &m, 1, CHUNK, spin == 0, spin != 0, T);
       if (spin == 0) {
-        const int64_t nn = T.nstep0[mi];
+        const int64_t nn = T.nstep0[0];
         if (nn == 0) continue;
-        const double* is = &T.invs0[(size_t)T.off0[mi]];
+        const double* is = &T.invs0[0];
         acc.assign((size_t)round_up(nn, CHUNK) * 4, 0.0);
         run_m<true>(spin, T, pairs, cr, mi, nm, nring, nullptr, acc.data(), leg);
         // a_l (l=m+2n) = eps_{l+1} At_n/g_n + eps_l At_{n-1}/g_{n-1}; a_{l+1} = Bt_n/g_n
@@ -685,10 +915,10 @@ void cpu_leg2alm(int spin, int64_t lmax, int64_t nm, const int64_t* mval, const 
         cd* ea = alm + mstart[mi];
         cd* ba = alm + alm_cstride + mstart[mi];
         for (int64_t l = m; l <= lmax && l < 2; ++l) ea[l] = 0, ba[l] = 0;
-        const int64_t nl = T.nstep2[mi];
+        const int64_t nl = T.nstep2[0];
         if (nl == 0) continue;
         const int64_t l0 = m > 2 ? m : 2;
-        const double* sg = &T.sig2[(size_t)T.off2[mi]];
+        const double* sg = &T.sig2[0];
         acc.assign((size_t)round_up(nl, CHUNK) * 4, 0.0);  // G+ (re,im), G- (re,im) per l
         run_m<true>(spin, T, pairs, cr, mi, nm, nring, nullptr, acc.data(), leg);
         for (int64_t j = 0; j < nl; ++j) {  // E = -sigma/2 (G+ + G-), B = i sigma/2 (G+ - G-)
@@ -702,48 +932,44 @@ void cpu_leg2alm(int spin, int64_t lmax, int64_t nm, const int64_t* mval, const 
   }
 }
 
+// Build (and keep) the FFT plans of these ring lengths, so that a timed region does not contain plan construction.
+// Ring lengths must be even (HEALPix: n = 4 r).
+int cpu_prepare_rings(int64_t nring, const int64_t* nphi) {
+  for (int64_t i = 0; i < nring; ++i)
+    if (nphi[i] <= 0 || (nphi[i] & 1)) return -1;
+  g_plans.prepare(nring, nphi);
+  return 0;
+}
+
 // leg [ncomp][nring][nm] -> map [ncomp][map_cstride]   (ringstart 0-based)
 void cpu_leg2map(int ncomp, int64_t nm, int64_t nring, const int64_t* nphi, const double* phi0,
                  const int64_t* ringstart, const double* leg_, double* map, int64_t map_cstride) {
   const cd* leg = reinterpret_cast<const cd*>(leg_);
-  PlanCache pc;
-  build_cache(pc, nring, nphi);
+  if (cpu_prepare_rings(nring, nphi)) std::abort();
 #pragma omp parallel
   {
-    std::vector<cd> hc, full, out, work;
+    std::vector<cd> hc, a, b, work;
 #pragma omp for schedule(dynamic, 4) collapse(2)
     for (int c = 0; c < ncomp; ++c)
       for (int64_t ir = 0; ir < nring; ++ir) {
-        const int64_t n = nphi[ir];
+        const int64_t n = nphi[ir], h = n / 2;
         const cd* row = leg + ((size_t)c * nring + ir) * nm;
-        hc.assign((size_t)(n / 2 + 1), cd(0, 0));
+        hc.assign((size_t)(h + 1), cd(0, 0));
         hc[0] = row[0].real();
         const cd step(std::cos(phi0[ir]), std::sin(phi0[ir]));
         cd cur(1, 0);
+        int64_t i1 = 0;   // m mod n, kept incrementally
         for (int64_t m = 1; m < nm; ++m) {
           // e^{i m phi0}: recomputed every 64 steps, multiplied up in between
           if ((m & 63) == 1) cur = cd(std::cos(m * phi0[ir]), std::sin(m * phi0[ir]));
           else cur *= step;
+          if (++i1 == n) i1 = 0;
           const cd t = row[m] * cur;
-          const int64_t i1 = m % n, i2 = (n - i1) % n;
-          if (i1 <= n / 2) hc[(size_t)i1] += t;
-          if (i2 <= n / 2) hc[(size_t)i2] += std::conj(t);
+          if (i1 <= h) hc[(size_t)i1] += t;
+          if (i1 == 0) hc[0] += std::conj(t);
+          else if (i1 >= h) hc[(size_t)(n - i1)] += std::conj(t);
         }
-        // ring[j] = sum_k c_k Re(hc[k] e^{2 pi i j k / n}): Hermitian-extend, conj, forward FFT, conj
-        full.assign((size_t)n, cd(0, 0));
-        full[0] = hc[0].real();
-        for (int64_t k = 1; k <= n / 2; ++k) {
-          if (2 * k == n) {
-            full[(size_t)k] = hc[(size_t)k].real();
-          } else {
-            full[(size_t)k] = std::conj(hc[(size_t)k]);
-            full[(size_t)(n - k)] = hc[(size_t)k];
-          }
-        }
-        out.resize((size_t)n);
-        fft_fwd(pc.get(n), full.data(), out.data(), work);
-        double* dst = map + (size_t)c * map_cstride + ringstart[ir];
-        for (int64_t j = 0; j < n; ++j) dst[j] = out[(size_t)j].real();
+        ring_c2r(*g_plans.ring(n), hc.data(), map + (size_t)c * map_cstride + ringstart[ir], a, b, work);
       }
   }
 }
@@ -752,27 +978,25 @@ void cpu_leg2map(int ncomp, int64_t nm, int64_t nring, const int64_t* nphi, cons
 void cpu_map2leg(int ncomp, int64_t nm, int64_t nring, const int64_t* nphi, const double* phi0,
                  const int64_t* ringstart, const double* map, int64_t map_cstride, double* leg_) {
   cd* leg = reinterpret_cast<cd*>(leg_);
-  PlanCache pc;
-  build_cache(pc, nring, nphi);
+  if (cpu_prepare_rings(nring, nphi)) std::abort();
 #pragma omp parallel
   {
-    std::vector<cd> in, X, work;
+    std::vector<cd> X, a, b, work;
 #pragma omp for schedule(dynamic, 4) collapse(2)
     for (int c = 0; c < ncomp; ++c)
       for (int64_t ir = 0; ir < nring; ++ir) {
-        const int64_t n = nphi[ir];
-        const double* src = map + (size_t)c * map_cstride + ringstart[ir];
-        in.resize((size_t)n);
-        for (int64_t j = 0; j < n; ++j) in[(size_t)j] = src[j];
-        X.resize((size_t)n);
-        fft_fwd(pc.get(n), in.data(), X.data(), work);
+        const int64_t n = nphi[ir], h = n / 2;
+        X.resize((size_t)(h + 1));
+        ring_r2c(*g_plans.ring(n), map + (size_t)c * map_cstride + ringstart[ir], X.data(), a, b, work);
         cd* row = leg + ((size_t)c * nring + ir) * nm;
         const cd step(std::cos(phi0[ir]), -std::sin(phi0[ir]));
         cd cur(1, 0);
+        int64_t i1 = 0;
         for (int64_t m = 0; m < nm; ++m) {
           if ((m & 63) == 0) cur = cd(std::cos(m * phi0[ir]), -std::sin(m * phi0[ir]));
-          row[m] = X[(size_t)(m % n)] * cur;
+          row[m] = (i1 <= h ? X[(size_t)i1] : std::conj(X[(size_t)(n - i1)])) * cur;
           cur *= step;
+          if (++i1 == n) i1 = 0;
         }
       }
   }

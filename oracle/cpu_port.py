@@ -1,8 +1,8 @@
 """FP64 CPU port of the hot path (TEST INFRASTRUCTURE / CPU BASELINE ONLY).
 
 Legendre stage: oracle/cpu_port.cpp (OpenMP, same formulation as the CUDA kernels).
-Ring stage: oracle/cpu_port.cpp too (alias fold / phase shift of SURVEY rows A8/A9 + a plain mixed-radix /
-Bluestein FFT per ring, OpenMP over rings).  Used by tests as a second, independent-in-precision
+Ring stage: oracle/cpu_port.cpp too (alias fold / phase shift of SURVEY rows A8/A9 + a real FFT per ring through a
+half-length mixed-radix / Bluestein complex transform, OpenMP over rings, plans kept between calls).  Used by tests as a second, independent-in-precision
 check of the formulation and by bench.py as the `cpu_baseline` / `--impl reference` arm
 ("kind": "port" — the real reference needs Julia + MPI + Ducc0, none of which exist here).
 """
@@ -80,6 +80,15 @@ def max_threads():
 
 def set_threads(n):
     lib().cpu_set_threads(C.c_int(int(n)))
+
+
+def prepare_rings(nphi):
+    """Build and keep the FFT plans of these (even) ring lengths: plan construction stays out of timed regions."""
+    nphi = np.ascontiguousarray(nphi, dtype=i64)
+    f = lib().cpu_prepare_rings
+    f.restype = C.c_int
+    if f(C.c_int64(len(nphi)), _p(nphi)):
+        raise ValueError("ring lengths must be positive and even")
 
 
 def leg2map(leg, nphi, phi0, rstart0, npix):
