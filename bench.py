@@ -195,6 +195,7 @@ class CpuPort:
     def _calibrate(self):
         mval = self.all_m[::max(1, (self.lmax + 1) // 16)]
         alm = self.rng.standard_normal((1, self.nalm)) + 1j * self.rng.standard_normal((1, self.nalm))
+        self.P.alm2leg(alm, 0, self.lmax, mval, self.mstart[mval], self.theta)  # cold pass: threads, pages
         t0 = time.perf_counter()
         self.P.alm2leg(alm, 0, self.lmax, mval, self.mstart[mval], self.theta)
         dt = time.perf_counter() - t0
