@@ -145,8 +145,10 @@ def test_fused_entry_points_are_bound():
         assert sym in bound, sym
 
 
-def test_blocks_balance_and_names_are_unique():
-    src = _strip_julia(open(JL).read())
+@pytest.mark.parametrize("path", [JL, os.path.join(ROOT, "tests", "golden", "make_reference_golden.jl"),
+                                  os.path.join(ROOT, "bench", "reference_cpu.jl")])
+def test_blocks_balance_and_names_are_unique(path):
+    src = _strip_julia(open(path).read())
     openers = {"module", "function", "struct", "if", "for", "while", "let", "begin", "try", "quote", "macro", "do"}
     depth, stack = 0, []
     for ln, line in enumerate(src.splitlines(), 1):
