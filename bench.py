@@ -202,10 +202,23 @@ class CpuPort:
         self.rate = self.P.legendre_steps(0, self.lmax, mval, self.theta)[0] / max(dt, 1e-9)
 
     def stride_for(self, budget_s):
+        """Sampling stride that makes one step_ms() call take about budget_s: a first guess from the calibrated
+        rate, then a trial pass at four times that stride (it also warms threads, pages and FFT plans) whose wall
+        time, input generation included, is scaled up."""
         if self.rate is None:
             self._calibrate()
         est = sum(self.full[0 if c == 1 else 2] * (1.0 if c == 1 else 4.3) for c, _ in self.transforms) / self.rate
-        return int(max(1, np.ceil(1.15 * est / max(budget_s, 1e-3))))
+        s1 = int(max(1, np.ceil(1.15 * est / max(budget_s, 1e-3))))
+        s, trial = s1, 4 * s1
+        for _ in range(3):   # the sparser the trial, the more its fixed costs inflate the estimate: refine
+            t0 = time.perf_counter()
+            self.step_ms(trial)
+            full = (time.perf_counter() - t0) * trial
+            s = int(max(1, np.ceil(1.2 * full / max(budget_s, 1e-3))))
+            if 2 * s >= trial:
+                break
+            trial = 2 * s
+        return s
 
     def step_ms(self, stride):
         P, lmax = self.P, self.lmax
@@ -508,7 +521,6 @@ def main():
         try:
             cpu = CpuPort(nside, lmax, transforms)
             stride = cpu.stride_for(args.cpu_budget)
-            cpu.step_ms(4 * stride)  # untimed: thread pool, first-touch pages and caches are cold on the first pass
             v, leg_ms, ring_ms = cpu.step_ms(stride)
             cpu_baseline = {"value": v, "unit": "ms", "cores": cpu.threads, "kind": "port", "extrapolated": stride > 1,
                             "sample_stride": stride, "sample": cpu.describe(stride, leg_ms, ring_ms)}
