@@ -206,3 +206,18 @@ def test_ring_blocks_are_cut_from_rank_independent_quantities(H, nside, P):
         assert hi[0, t] == nr and lo[nb - 1, t] == 0            # pole-most block ends the local list, equator-most starts it
         assert np.all(hi[1:, t] == lo[:-1, t]) and np.all(hi[:, t] >= lo[:, t])
     assert int((hi - lo).sum()) == 4 * nside - 1
+    # A block is a collective: on every rank it must hold the rings of ONE range of north/south pairs (distance
+    # from the equator), the ranges of different blocks must not overlap, and both rings of a pair must sit in
+    # the same block of the same rank.
+    dist = [np.abs(np.asarray(H.get_rindexes_RR(nside, t, P), dtype=np.int64) - eq) for t in range(P)]
+    prev_min = None
+    for b in range(nb):          # b = 0 is the pole-most block
+        d = np.concatenate([dist[t][lo[b, t]:hi[b, t]] for t in range(P)])
+        assert d.size > 0
+        vals, counts = np.unique(d, return_counts=True)
+        assert np.array_equal(vals, np.arange(vals[0], vals[-1] + 1))          # one contiguous pair range
+        assert np.all(counts[vals > 0] == 2) and np.all(counts[vals == 0] == 1)  # N and S ring together
+        if prev_min is not None:
+            assert vals[-1] < prev_min
+        prev_min = vals[0]
+    assert prev_min == 0
