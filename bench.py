@@ -583,7 +583,7 @@ def parity_block(plan, H, torch, dist, world, rank, nside, lmax, ncomps, seed0, 
         if out["rings_vs_oracle"] else None
     out["ok"] = bool(ok)
     out["what"] = ("adjointness: |<f,Ya> - <Y^T f,a>_w| / (|f| |Ya|), all ranks; rings_vs_oracle: relative L2 of rank 0's "
-                   "sampled rings of Y a against oracle/sht_oracle.c (long double; reference ring cut and pair "
+                   "sampled rings of Y a against oracle/sht_oracle.c (long double, __float128 on the rings next to the poles; reference ring cut and pair "
                    "colatitude applied, oracle/parity.py)")
     return out
 

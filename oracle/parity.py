@@ -1,4 +1,5 @@
-"""Sampled parity checks of a plan against the long-double oracle (TEST INFRASTRUCTURE ONLY).
+"""Sampled parity checks of a plan against the extended-precision oracle (long double; __float128 recurrences on
+the rings next to the poles) -- TEST INFRASTRUCTURE ONLY.
 
 Used by tests/test_gpu_headline.py and by bench.py's `parity` block (after the timed region).  The oracle
 applies the reference backend's m > mlim(theta) ring cut so that the comparison measures the
