@@ -5,8 +5,8 @@
 //   Legendre stage (cpu_alm2leg / cpu_leg2alm): on-the-fly scaled recurrences (cos^2 two-term form for
 //     spin 0, rescaled three-term form for spin +-2) in the accuracy classes of
 //     csrc/legendre_tables.hpp (X / Y standard forms, DP / DE difference forms), north/south ring
-//     pairing, m > mlim(theta) culling, 2^(800 k) range tracking with a warp-like block of W ring pairs
-//     advancing in lock step;
+//     pairing, m > mlim(theta) culling, 2^(800 k) range tracking with a warp-like block of ring pairs (4 SIMD
+//     vectors for spin 0, 2 for spin 2, held in registers) advancing in lock step;
 //   ring stage (cpu_leg2map / cpu_map2leg): phase shift + alias fold + a real FFT per ring through
 //     one half-length complex transform (plain mixed radix, Bluestein for what is left of the length after the
 //     factors 2, 3, 5); plans are built once per length and kept.
