@@ -259,3 +259,30 @@ def test_cpu_port_high_lmax_sampled(O, P):
         assert np.all(per_ring[polar & north] < 5e-14), per_ring
         assert np.all(per_ring[north] < 3e-13), per_ring
         assert np.all(per_ring < 1e-12), per_ring
+
+
+def test_cpu_port_polar_rings_at_headline_lmax(O, P):
+    """(4096, 8191), the rings next to the north pole, all m below the backend's ring cut: the FP64 port (polar
+    difference form, same formulation as the kernels) against the oracle (these rings in __float128).  Measured
+    <= 2.7e-14; the same comparison against the plain long-double oracle of round 1 read 4e-13, which was the
+    oracle's own error (profiles/r02_parity.md)."""
+    nside, lmax = 4096, 8191
+    rings = np.array([1, 2, 3, 4, 5, 8, 16, 30, 64, 300])
+    nphi, theta, phi0, fp = O.healpix_rings(nside, rings)
+    mval = np.arange(lmax + 1, dtype=np.int64)
+    mstart0 = O.rr_mstart1(lmax, 1, mval) - 1
+    nalm = int(mstart0[-1] + lmax + 1)
+    rng = np.random.default_rng(8191)
+    for spin in (0, 2):
+        nc = 1 if spin == 0 else 2
+        alm = rng.standard_normal((nc, nalm)) + 1j * rng.standard_normal((nc, nalm))
+        lp = P.alm2leg(alm, spin, lmax, mval, mstart0, theta)
+        O.set_reference_cut(True)
+        try:
+            lo = O.alm2leg(alm, spin, lmax, mval, mstart0, theta)
+        finally:
+            O.set_reference_cut(False)
+        num = np.sum(np.abs(lp - lo.astype(np.complex128)) ** 2, axis=(0, 2))
+        den = np.sum(np.abs(lo) ** 2, axis=(0, 2)).astype(float)
+        per_ring = np.sqrt(num / den)
+        assert np.all(per_ring < 1e-13), (spin, per_ring)
