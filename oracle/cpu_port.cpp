@@ -47,6 +47,7 @@ const double SC_DOWN = std::ldexp(1.0, -800);
 struct Pair {
   double cth, sth, sh, ch;  // cos/sin(theta_north), sin/cos(theta_north/2)
   double x2, s2, y2;        // cos^2, sin^2, 2 sin^2(theta/2), each rounded once from long double
+  double sthl;              // sin(theta) - sth (only used by the double-double start value experiment)
   double theta;
   int64_t irN, irS;         // ring slots (irS = -1: unpaired)
   int64_t mlim0, mlim2;
@@ -71,6 +72,7 @@ std::vector<Pair> make_pairs(int64_t lmax, int64_t nring, const double* theta) {
     p.x2 = (double)(c * c);
     p.s2 = (double)(sn * sn);
     p.y2 = (double)(2.0L * shl * shl);
+    p.sthl = (double)(sn - (long double)p.sth);
     p.theta = theta[n];
     p.irN = n;
     p.irS = s;
@@ -119,6 +121,44 @@ inline double frexp_fast(double x, int* e) {
   return x;
 }
 
+// EXPERIMENT (cpu_set_dd_start, off by default so that the port keeps modelling the kernels): the start value
+// sin(theta)^m in double-double arithmetic.  Repeated squaring in double doubles the rounding error of every earlier
+// squaring, i.e. the start value -- and with it the whole (m, ring) row -- is off by up to m * 1.1e-16 = 9e-13 at
+// m = 8191; measured, it is what sets the worst mid-latitude rings (2.7e-13 -> 4e-14, profiles/r02_parity.md).
+int g_dd_start = 0;
+inline void dd_mul(double ah, double al, double bh, double bl, double& ch, double& cl) {
+  const double p = ah * bh;
+  const double e = std::fma(ah, bh, -p) + (ah * bl + al * bh);
+  ch = p + e;
+  cl = e - (ch - p);
+}
+inline void pow_scaled_dd(double base, double base_lo, int64_t n, double& mant, int64_t& e) {
+  int be;
+  double bh = frexp_fast(base, &be);
+  double bl = std::ldexp(base_lo, -be);
+  int64_t bexp = be;
+  double mh = 1.0, ml = 0.0;
+  e = 0;
+  while (n > 0) {
+    int t;
+    if (n & 1) {
+      dd_mul(mh, ml, bh, bl, mh, ml);
+      e += bexp;
+      const double r = frexp_fast(mh, &t);
+      ml = std::ldexp(ml, -t);
+      mh = r;
+      e += t;
+    }
+    dd_mul(bh, bl, bh, bl, bh, bl);
+    bexp *= 2;
+    const double r = frexp_fast(bh, &t);
+    bl = std::ldexp(bl, -t);
+    bh = r;
+    bexp += t;
+    n >>= 1;
+  }
+  mant = mh + ml;
+}
 // x^n (n >= 0) as mant * 2^e with mant in [0.5,1) (or 0)
 inline void pow_scaled(double base, int64_t n, double& mant, int64_t& e) {
   int be;
@@ -243,7 +283,8 @@ void block_s0(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool ysin,
     y[w] = ysin ? pr.s2 : pr.x2;
     double mant;
     int64_t e;
-    pow_scaled(pr.sth, m, mant, e);
+    if (g_dd_start) pow_scaled_dd(pr.sth, pr.sthl, m, mant, e);
+    else pow_scaled(pr.sth, m, mant, e);
     to_scaled(k0 * mant, e, u[w], sc[w]);
     if (!act[w]) u[w] = 0.0, sc[w] = 0;
     v[w] = DIFF ? u[w] : 0.0;
@@ -378,7 +419,8 @@ void block_s2(const std::vector<Pair>& pairs, int64_t p0, int64_t p1, bool yform
     y[w] = yform ? -pr.y2 : pr.cth;
     double mant;
     int64_t e;
-    pow_scaled(pr.sth, pw, mant, e);
+    if (g_dd_start) pow_scaled_dd(pr.sth, pr.sthl, pw, mant, e);
+    else pow_scaled(pr.sth, pw, mant, e);
     double fs = 1.0, fc = 1.0;
     for (int k = 0; k < q; ++k) {
       fs *= pr.sh * pr.sh;
@@ -798,6 +840,7 @@ void ring_r2c(const RingPlan& R, const double* x, cd* X, std::vector<cd>& a, std
 extern "C" {
 
 int cpu_max_threads(void) { return omp_get_max_threads(); }
+void cpu_set_dd_start(int on) { g_dd_start = on; }
 void cpu_set_threads(int n) {
   if (n > 0) omp_set_num_threads(n);
 }

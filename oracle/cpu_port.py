@@ -78,6 +78,11 @@ def max_threads():
     return int(f())
 
 
+def set_dd_start(on):
+    """Experiment switch: start values sin(theta)^m in double-double arithmetic (off = what the kernels do)."""
+    lib().cpu_set_dd_start(C.c_int(1 if on else 0))
+
+
 def set_threads(n):
     lib().cpu_set_threads(C.c_int(int(n)))
 
